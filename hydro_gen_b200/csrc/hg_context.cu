@@ -1,0 +1,465 @@
+// hg_context.cu — the C ABI of include/hydrogen_b200.h: context lifetime, settings,
+// field transfer in the reference's RGBA32F texture format, the per-step dispatch
+// schedule of src/erosion.cpp:76-200 and the main-loop rule of src/main.cpp:310-324.
+#include <stdarg.h>
+#include <new>
+#include "hg_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void hg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* hg_last_error(void) { return g_err; }
+extern "C" const char* hg_version(void) { return "hydrogen_b200 0.1 sm_100a"; }
+
+// ------------------------------------------------------------------ lifetime
+
+static void free_ctx(hg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    hg_slab_disconnect(c);
+    if (c->arena) cudaFree(c->arena);
+    if (c->aux) cudaFree(c->aux);
+    if (c->particles) cudaFree(c->particles);
+    if (c->lockmap) cudaFree(c->lockmap);
+    if (c->staging) cudaFree(c->staging);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int refresh_params(hg_ctx* c) {
+    c->sp = hg_make_step_params(c->erosion);
+    return HG_OK;
+}
+
+int hg_ensure_aux(hg_ctx* c) {
+    if (c->aux) return HG_OK;
+    size_t bytes = (size_t)HG_NAUX * c->g.plane_elems * sizeof(float);
+    HG_CUDA(cudaMalloc(&c->aux, bytes));
+    HG_CUDA(cudaMemsetAsync(c->aux, 0, bytes, c->stream));
+    return HG_OK;
+}
+
+static int create_impl(hg_ctx* c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        hg_set_error("no CUDA device available (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return HG_ERR_NO_DEVICE;
+    }
+    if (c->device < 0 || c->device >= ndev) { hg_set_error("device %d out of range (%d devices)", c->device, ndev); return HG_ERR_INVALID; }
+    HG_CUDA(cudaSetDevice(c->device));
+    HG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    HG_CUDA(cudaEventCreate(&c->ev0));
+    HG_CUDA(cudaEventCreate(&c->ev1));
+    // arena = 2 sets x 9 planes, then one 4 KiB page of halo flags
+    c->arena_bytes = (size_t)2 * HG_NPLANES * c->g.plane_elems * sizeof(float) + 4096;
+    HG_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+    HG_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
+    HG_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+    HG_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (c->particle_count) {
+        // gl::gen_buffer(particle_buffer, particle_count * sizeof(Particle)), state.cpp:28-30; zeroed (hazard 6)
+        HG_CUDA(cudaMalloc(&c->particles, (size_t)c->particle_count * sizeof(hg_particle)));
+        HG_CUDA(cudaMemsetAsync(c->particles, 0, (size_t)c->particle_count * sizeof(hg_particle), c->stream));
+    }
+    if (c->erosion_type == HG_PARTICLES) {
+        int rc = hg_ensure_aux(c);   // momentum map + thermal planes
+        if (rc) return rc;
+    }
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0, uint32_t rows,
+                                  uint32_t particle_count, int erosion_type, int device) {
+    if (map_w == 0 || map_h == 0 || map_w % HG_WRKGRP || map_h % HG_WRKGRP) {
+        hg_set_error("map size %ux%u must be a positive multiple of %d (the reference dispatches map/8 groups)", map_w, map_h, HG_WRKGRP);
+        return nullptr;
+    }
+    if (map_w > 1u << 20 || map_h > 1u << 20) { hg_set_error("map size %ux%u too large", map_w, map_h); return nullptr; }
+    if (rows == 0 || (uint64_t)row0 + rows > map_h) { hg_set_error("slab rows [%u,%u) outside map height %u", row0, row0 + rows, map_h); return nullptr; }
+    if (erosion_type != HG_GRID && erosion_type != HG_PARTICLES) { hg_set_error("unknown erosion type %d", erosion_type); return nullptr; }
+    if (erosion_type == HG_PARTICLES && (row0 != 0 || rows != map_h)) { hg_set_error("particle mode runs on a whole map only"); return nullptr; }
+    if (erosion_type == HG_PARTICLES && particle_count == 0) { hg_set_error("particle mode needs particle_count > 0"); return nullptr; }
+    hg_ctx* c = new (std::nothrow) hg_ctx();
+    if (!c) { hg_set_error("out of host memory"); return nullptr; }
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->erosion_type = erosion_type;
+    c->schedule = HG_SCHEDULE_FUSED;
+    c->particle_count = particle_count;
+    c->g.W = (int)map_w; c->g.H = (int)map_h;
+    c->g.row0 = (int)row0; c->g.rows = (int)rows;
+    c->g.pitch = (int)map_w;
+    c->g.rows_alloc = (int)rows + 2 * HG_HALO_ROWS;
+    c->g.plane_elems = (size_t)c->g.rows_alloc * c->g.pitch;
+    c->erosion = hg_default_erosion(erosion_type == HG_PARTICLES, particle_count);
+    c->rain = hg_default_rain();
+    c->map = hg_default_map(0.0f);
+    refresh_params(c);
+    if (create_impl(c) != HG_OK) { free_ctx(c); return nullptr; }
+    return c;
+}
+
+extern "C" hg_ctx* hg_create(uint32_t map_w, uint32_t map_h, uint32_t particle_count, int erosion_type, int device) {
+    return hg_create_slab(map_w, map_h, 0, map_h, particle_count, erosion_type, device);
+}
+
+extern "C" void hg_destroy(hg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_ctx(ctx);
+}
+
+// ------------------------------------------------------------------ settings
+
+extern "C" int hg_set_erosion(hg_ctx* c, const hg_erosion_data* d) {
+    HG_CHECK_CTX(c);
+    if (!d) { hg_set_error("null settings"); return HG_ERR_INVALID; }
+    c->erosion = *d;
+    return refresh_params(c);
+}
+extern "C" int hg_set_rain(hg_ctx* c, const hg_rain_data* d) {
+    HG_CHECK_CTX(c);
+    if (!d) { hg_set_error("null settings"); return HG_ERR_INVALID; }
+    c->rain = *d;
+    return HG_OK;
+}
+extern "C" int hg_set_map(hg_ctx* c, const hg_map_settings_data* d) {
+    HG_CHECK_CTX(c);
+    if (!d) { hg_set_error("null settings"); return HG_ERR_INVALID; }
+    c->map = *d;
+    return HG_OK;
+}
+extern "C" int hg_get_erosion(hg_ctx* c, hg_erosion_data* o) { HG_CHECK_CTX(c); if (!o) return HG_ERR_INVALID; *o = c->erosion; return HG_OK; }
+extern "C" int hg_get_rain(hg_ctx* c, hg_rain_data* o) { HG_CHECK_CTX(c); if (!o) return HG_ERR_INVALID; *o = c->rain; return HG_OK; }
+extern "C" int hg_get_map(hg_ctx* c, hg_map_settings_data* o) { HG_CHECK_CTX(c); if (!o) return HG_ERR_INVALID; *o = c->map; return HG_OK; }
+
+extern "C" int hg_set_schedule(hg_ctx* c, int schedule) {
+    HG_CHECK_CTX(c);
+    if (schedule != HG_SCHEDULE_FUSED && schedule != HG_SCHEDULE_PASSES) { hg_set_error("unknown schedule %d", schedule); return HG_ERR_INVALID; }
+    if (schedule == HG_SCHEDULE_PASSES && c->schedule != HG_SCHEDULE_PASSES) {
+        if (c->g.row0 != 0 || c->g.rows != c->g.H) { hg_set_error("the PASSES schedule runs on a whole map only"); return HG_ERR_STATE; }
+        int rc = hg_ensure_aux(c);
+        if (rc) return rc;
+        if (c->erosion_type == HG_GRID) {   // H.a was not maintained by the fused schedule
+            c->schedule = schedule;
+            return hg_fill_total(c);
+        }
+    }
+    c->schedule = schedule;
+    return HG_OK;
+}
+
+// ------------------------------------------------------------- field transfer
+
+namespace {
+
+struct Chan4 { float* p[4]; };   // nullptr = channel not stored (reads as 0 / write ignored)
+
+// dst/src RGBA32F rows [r0, r0+nr) of the slab <-> planes (local row = slab row + HG_HALO_ROWS)
+__global__ void __launch_bounds__(256) k_pack(Chan4 ch, int W, int pitch, int r0, int nr, float4* out, int synth_total) {
+    size_t n = (size_t)nr * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / W), x = (int)(i - (size_t)r * W);
+        size_t s = (size_t)(r0 + r + HG_HALO_ROWS) * pitch + x;
+        float4 v;
+        v.x = ch.p[0] ? ch.p[0][s] : 0.0f;
+        v.y = ch.p[1] ? ch.p[1][s] : 0.0f;
+        v.z = ch.p[2] ? ch.p[2][s] : 0.0f;
+        v.w = ch.p[3] ? ch.p[3][s] : 0.0f;
+        if (synth_total) v.w = v.x + v.y + v.z;   // H.a as the last writer of a step leaves it
+        out[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack(Chan4 ch, int W, int pitch, int r0, int nr, const float4* in) {
+    size_t n = (size_t)nr * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / W), x = (int)(i - (size_t)r * W);
+        size_t s = (size_t)(r0 + r + HG_HALO_ROWS) * pitch + x;
+        float4 v = in[i];
+        if (ch.p[0]) ch.p[0][s] = v.x;
+        if (ch.p[1]) ch.p[1][s] = v.y;
+        if (ch.p[2]) ch.p[2][s] = v.z;
+        if (ch.p[3]) ch.p[3][s] = v.w;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mass(const float* rock, const float* dirt, const float* water, const float* sr, const float* sd,
+                                              int W, int pitch, int rows, double* out) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    size_t n = (size_t)rows * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(i / W), x = (int)(i - (size_t)r * W);
+        size_t s = (size_t)(r + HG_HALO_ROWS) * pitch + x;
+        acc[0] += rock[s]; acc[1] += dirt[s]; acc[2] += water[s]; acc[3] += sr[s]; acc[4] += sd[s];
+    }
+    __shared__ double sh[5][8];
+    for (int k = 0; k < 5; k++) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double v = 0;
+        for (int w = 0; w < 8; w++) v += sh[threadIdx.x][w];
+        atomicAdd(out + threadIdx.x, v);
+    }
+}
+
+int field_channels(hg_ctx* c, int field, Chan4* ch, int* synth_total, bool for_write) {
+    *synth_total = 0;
+    for (int k = 0; k < 4; k++) ch->p[k] = nullptr;
+    switch (field) {
+    case HG_FIELD_HEIGHTMAP:
+        ch->p[0] = hg_cur(c, PL_ROCK, 1); ch->p[1] = hg_cur(c, PL_DIRT, 1); ch->p[2] = hg_cur(c, PL_WATER, 1);
+        if (hg_total_live(c)) ch->p[3] = hg_total(c, 1);
+        else if (!for_write) *synth_total = 1;
+        return HG_OK;
+    case HG_FIELD_FLUX:
+        for (int k = 0; k < 4; k++) ch->p[k] = hg_cur(c, PL_FL + k, 1);
+        return HG_OK;
+    case HG_FIELD_SEDIMENT:
+        ch->p[0] = hg_cur(c, PL_SR, 1); ch->p[1] = hg_cur(c, PL_SD, 1);
+        return HG_OK;
+    case HG_FIELD_VELOCITY:
+        if (!c->aux) { hg_set_error("velocity is not materialised by the FUSED schedule (it is dead between steps); use HG_SCHEDULE_PASSES"); return HG_ERR_STATE; }
+        for (int k = 0; k < 4; k++) ch->p[k] = hg_vel(c, k, 1);
+        return HG_OK;
+    case HG_FIELD_THERMAL_C:
+    case HG_FIELD_THERMAL_D:
+        if (!c->aux) { hg_set_error("thermal outflow is not materialised by the FUSED schedule; use HG_SCHEDULE_PASSES"); return HG_ERR_STATE; }
+        for (int k = 0; k < 4; k++) ch->p[k] = hg_aux_plane(c, (field == HG_FIELD_THERMAL_C ? AX_TC : AX_TD) + k);
+        return HG_OK;
+    default:
+        hg_set_error("unknown field %d", field);
+        return HG_ERR_INVALID;
+    }
+}
+
+int ensure_staging(hg_ctx* c) {
+    if (c->staging) return HG_OK;
+    size_t want = (size_t)32 << 20;                       // 32 Mi floats = 128 MiB
+    size_t need = (size_t)c->g.rows * c->g.W * 4;
+    c->staging_elems = need < want ? need : want;
+    size_t row = (size_t)c->g.W * 4;
+    if (c->staging_elems < row) c->staging_elems = row;
+    HG_CUDA(cudaMalloc(&c->staging, c->staging_elems * sizeof(float)));
+    return HG_OK;
+}
+
+int transfer(hg_ctx* c, int field, float* host, bool upload) {
+    if (!host) { hg_set_error("null host buffer"); return HG_ERR_INVALID; }
+    Chan4 ch; int synth;
+    int rc = field_channels(c, field, &ch, &synth, upload);
+    if (rc) return rc;
+    rc = ensure_staging(c);
+    if (rc) return rc;
+    int W = c->g.W;
+    int rows_per = (int)(c->staging_elems / ((size_t)W * 4));
+    for (int r0 = 0; r0 < c->g.rows; r0 += rows_per) {
+        int nr = c->g.rows - r0 < rows_per ? c->g.rows - r0 : rows_per;
+        size_t n = (size_t)nr * W;
+        int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+        float* hp = host + (size_t)r0 * W * 4;
+        if (upload) {
+            HG_CUDA(cudaMemcpyAsync(c->staging, hp, n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            k_unpack<<<blocks, 256, 0, c->stream>>>(ch, W, c->g.pitch, r0, nr, reinterpret_cast<const float4*>(c->staging));
+            HG_LAUNCH_CHECK(c);
+        } else {
+            k_pack<<<blocks, 256, 0, c->stream>>>(ch, W, c->g.pitch, r0, nr, reinterpret_cast<float4*>(c->staging), synth);
+            HG_LAUNCH_CHECK(c);
+            HG_CUDA(cudaMemcpyAsync(hp, c->staging, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    return HG_OK;
+}
+
+}  // namespace
+
+extern "C" int hg_upload_async(hg_ctx* c, int field, const float* src) { HG_CHECK_CTX(c); return transfer(c, field, const_cast<float*>(src), true); }
+extern "C" int hg_download_async(hg_ctx* c, int field, float* dst) { HG_CHECK_CTX(c); return transfer(c, field, dst, false); }
+extern "C" int hg_upload(hg_ctx* c, int field, const float* src) {
+    int rc = hg_upload_async(c, field, src);
+    if (rc) return rc;
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+extern "C" int hg_download(hg_ctx* c, int field, float* dst) {
+    int rc = hg_download_async(c, field, dst);
+    if (rc) return rc;
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_slab_set_ghost(hg_ctx* c, int field, int side, const float* rows) {
+    HG_CHECK_CTX(c);
+    if (!rows || (side != 0 && side != 1)) { hg_set_error("bad ghost upload"); return HG_ERR_INVALID; }
+    Chan4 ch; int synth;
+    int rc = field_channels(c, field, &ch, &synth, true);
+    if (rc) return rc;
+    rc = ensure_staging(c);
+    if (rc) return rc;
+    size_t n = (size_t)HG_HALO_ROWS * c->g.W;
+    if (n * 4 > c->staging_elems) { hg_set_error("staging too small for ghost rows"); return HG_ERR_STATE; }
+    HG_CUDA(cudaMemcpyAsync(c->staging, rows, n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int r0 = side == 0 ? -HG_HALO_ROWS : c->g.rows;
+    k_unpack<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(ch, c->g.W, c->g.pitch, r0, HG_HALO_ROWS, reinterpret_cast<const float4*>(c->staging));
+    HG_LAUNCH_CHECK(c);
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_upload_particles(hg_ctx* c, const hg_particle* src, uint32_t count) {
+    HG_CHECK_CTX(c);
+    if (!src || count > c->particle_count) { hg_set_error("bad particle upload (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
+    HG_CUDA(cudaMemcpyAsync(c->particles, src, (size_t)count * sizeof(hg_particle), cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+extern "C" int hg_download_particles(hg_ctx* c, hg_particle* dst, uint32_t count) {
+    HG_CHECK_CTX(c);
+    if (!dst || count > c->particle_count) { hg_set_error("bad particle download (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
+    HG_CUDA(cudaMemcpyAsync(dst, c->particles, (size_t)count * sizeof(hg_particle), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+extern "C" void* hg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { hg_set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void hg_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int hg_mass(hg_ctx* c, double out5[5]) {
+    HG_CHECK_CTX(c);
+    if (!out5) return HG_ERR_INVALID;
+    double* d = reinterpret_cast<double*>(c->d_counters + 2);
+    HG_CUDA(cudaMemsetAsync(d, 0, 5 * sizeof(double), c->stream));
+    k_mass<<<148 * 8, 256, 0, c->stream>>>(hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1),
+                                           hg_cur(c, PL_SR, 1), hg_cur(c, PL_SD, 1), c->g.W, c->g.pitch, c->g.rows, d);
+    HG_LAUNCH_CHECK(c);
+    HG_CUDA(cudaMemcpyAsync(out5, d, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+// ------------------------------------------------------- streams, sync, timing
+
+extern "C" int hg_sync(hg_ctx* c) { HG_CHECK_CTX(c); HG_CUDA(cudaStreamSynchronize(c->stream)); return HG_OK; }
+extern "C" int hg_set_stream(hg_ctx* c, void* s) {
+    HG_CHECK_CTX(c);
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = static_cast<cudaStream_t>(s);
+    return HG_OK;
+}
+extern "C" void* hg_get_stream(hg_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+extern "C" int hg_timer_start(hg_ctx* c) { HG_CHECK_CTX(c); HG_CUDA(cudaEventRecord(c->ev0, c->stream)); return HG_OK; }
+extern "C" int hg_timer_stop(hg_ctx* c, float* ms) {
+    HG_CHECK_CTX(c);
+    HG_CUDA(cudaEventRecord(c->ev1, c->stream));
+    HG_CUDA(cudaEventSynchronize(c->ev1));
+    if (ms) HG_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return HG_OK;
+}
+extern "C" uint64_t hg_launch_count(hg_ctx* c) { return c ? c->launches : 0; }
+extern "C" int hg_far_fetch_count(hg_ctx* c, uint64_t* cells) {
+    HG_CHECK_CTX(c);
+    unsigned long long v = 0;
+    HG_CUDA(cudaMemcpyAsync(&v, c->d_counters, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(v), c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (cells) *cells = v;
+    return HG_OK;
+}
+
+// -------------------------------------------------------------------- dispatch
+
+extern "C" int hg_gen_heightmap(hg_ctx* c) { HG_CHECK_CTX(c); return hg_launch_heightmap(c); }
+
+extern "C" int hg_dispatch_grid_rain(hg_ctx* c, float time) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_GRID) { hg_set_error("dispatch_grid_rain on a particle context (prog.grid is null in the reference)"); return HG_ERR_STATE; }
+    return hg_launch_rain(c, time);
+}
+
+extern "C" int hg_dispatch_grid(hg_ctx* c) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_GRID) { hg_set_error("dispatch_grid on a particle context"); return HG_ERR_STATE; }
+    if (c->schedule == HG_SCHEDULE_PASSES) return hg_launch_passes_step(c);
+    int rc = hg_launch_fused_step(c);
+    if (rc) return rc;
+    return hg_slab_exchange(c);
+}
+
+extern "C" int hg_dispatch_pass(hg_ctx* c, int pass) {
+    HG_CHECK_CTX(c);
+    if (c->schedule != HG_SCHEDULE_PASSES) { hg_set_error("hg_dispatch_pass needs HG_SCHEDULE_PASSES"); return HG_ERR_STATE; }
+    return hg_launch_pass(c, pass);
+}
+
+extern "C" int hg_dispatch_particle_pass(hg_ctx* c, int which, float time, int should_rain) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_PARTICLES) { hg_set_error("particle pass on a grid context"); return HG_ERR_STATE; }
+    return which == 0 ? hg_launch_particle_move(c, time, should_rain) : hg_launch_particle_erode(c);
+}
+
+// Erosion::dispatch_particle, src/erosion.cpp:132-156
+extern "C" int hg_dispatch_particle(hg_ctx* c, float time, int should_rain) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_PARTICLES) { hg_set_error("dispatch_particle on a grid context"); return HG_ERR_STATE; }
+    int rc = hg_launch_particle_move(c, time, should_rain);
+    if (rc) return rc;
+    rc = hg_launch_particle_erode(c);
+    if (rc) return rc;
+    return hg_launch_thermal_smooth_particle(c);
+}
+
+// src/main.cpp:310-324
+extern "C" int hg_run(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int should_rain) {
+    HG_CHECK_CTX(c);
+    for (uint32_t k = 0; k < n_steps; k++) {
+        float time = time0 + (float)k * dtime;
+        c->erosion_steps++;
+        int rc;
+        if (c->erosion_type == HG_GRID) {
+            if (should_rain && c->rain.period != 0 && !(c->erosion_steps % (uint32_t)c->rain.period)) {
+                rc = hg_dispatch_grid_rain(c, time);
+                if (rc) return rc;
+            }
+            rc = hg_dispatch_grid(c);
+        } else {
+            rc = hg_dispatch_particle(c, time, should_rain);
+        }
+        if (rc) return rc;
+    }
+    return HG_OK;
+}
+extern "C" int hg_get_steps(hg_ctx* c, uint32_t* s) { HG_CHECK_CTX(c); if (!s) return HG_ERR_INVALID; *s = c->erosion_steps; return HG_OK; }
+extern "C" int hg_set_steps(hg_ctx* c, uint32_t s) { HG_CHECK_CTX(c); c->erosion_steps = s; return HG_OK; }
+
+#ifndef HG_WITH_GL
+extern "C" int hg_register_gl(hg_ctx*, const unsigned[2], const unsigned[2]) {
+    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image)");
+    return HG_ERR_STATE;
+}
+extern "C" int hg_publish_gl(hg_ctx*, int) {
+    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image)");
+    return HG_ERR_STATE;
+}
+#endif

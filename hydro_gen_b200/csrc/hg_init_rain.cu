@@ -1,0 +1,77 @@
+// hg_init_rain.cu — heightmap initialisation (State::World::gen_heightmap,
+// src/state.cpp:116-147 -> glsl/heightmap.glsl) and rain (Erosion::dispatch_grid_rain,
+// src/erosion.cpp:76-89 -> glsl/rain.glsl).  Both are pointwise in the GLOBAL cell
+// coordinate and ALU-bound (32 gradient-noise / 8 simplex evaluations per cell), so a
+// slab simply evaluates its own rows plus its ghost rows: no exchange is needed.
+#include "hg_internal.cuh"
+#include "hg_noise.cuh"
+
+namespace {
+
+struct SlabDom { int W, H, pitch, row0, rows; };
+
+// local row index (ghost rows first) of global row gy
+__device__ __forceinline__ size_t sidx(const SlabDom& d, int x, int gy) {
+    return (size_t)(gy - d.row0 + HG_HALO_ROWS) * d.pitch + x;
+}
+
+struct InitArgs { float *rock, *dirt, *water, *total, *zero[10]; int nzero; };
+
+__global__ void __launch_bounds__(256) k_heightmap(SlabDom d, hg_map_settings_data cfg, InitArgs A) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int gy = d.row0 - HG_HALO_ROWS + (int)(blockIdx.y * blockDim.y + threadIdx.y);
+    if (x >= d.W || gy < 0 || gy >= d.H || gy >= d.row0 + d.rows + HG_HALO_ROWS) return;
+    float rock, dirt;
+    hg_heightmap_cell(cfg, x, gy, d.W, d.H, rock, dirt);
+    size_t i = sidx(d, x, gy);
+    A.rock[i] = rock;
+    A.dirt[i] = dirt;
+    A.water[i] = 0.0f;
+    if (A.total) A.total[i] = rock + dirt + 0.0f;
+    for (int k = 0; k < A.nzero; k++) A.zero[k][i] = 0.0f;
+}
+
+struct RainArgs { const float *rock, *dirt, *water, *total; float *o_rock, *o_dirt, *o_water, *o_total; };
+
+__global__ void __launch_bounds__(256) k_rain(SlabDom d, hg_rain_data set, hg_map_settings_data map_set, float time, RainArgs A) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int gy = d.row0 - HG_HALO_ROWS + (int)(blockIdx.y * blockDim.y + threadIdx.y);
+    if (x >= d.W || gy < 0 || gy >= d.H || gy >= d.row0 + d.rows + HG_HALO_ROWS) return;
+    size_t i = sidx(d, x, gy);
+    float rock = A.rock[i], dirt = A.dirt[i], water = A.water[i];
+    // H.a as its last writer left it: (rock + dirt) + water (smoothing.glsl:101, rain.glsl:54,
+    // heightmap.glsl:146); read back when the PASSES schedule materialises it
+    float total = A.total ? A.total[i] : rock + dirt + water;
+    water += hg_rain_cell(set, map_set, time, x, gy, total);
+    A.o_rock[i] = rock; A.o_dirt[i] = dirt; A.o_water[i] = water;
+    if (A.o_total) A.o_total[i] = rock + dirt + water;
+}
+
+}  // namespace
+
+int hg_launch_heightmap(hg_ctx* c) {
+    SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
+    dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
+    InitArgs A{};
+    // gen_heightmap writes the WRITE textures of heightmap, velocity, flux, sediment, then swaps all four
+    A.rock = hg_cur(c, PL_ROCK, 0); A.dirt = hg_cur(c, PL_DIRT, 0); A.water = hg_cur(c, PL_WATER, 0);
+    A.total = c->aux ? hg_total(c, 0) : nullptr;   // kept current whenever the planes exist
+    A.nzero = 0;
+    for (int p = PL_FL; p <= PL_SD; p++) A.zero[A.nzero++] = hg_cur(c, p, 0);
+    if (c->aux) for (int ch = 0; ch < 4; ch++) A.zero[A.nzero++] = hg_vel(c, ch, 0);
+    k_heightmap<<<g, b, 0, c->stream>>>(d, c->map, A);
+    HG_LAUNCH_CHECK(c);
+    c->ri[0] ^= 1; c->ri[1] ^= 1; c->ri[2] ^= 1; c->ri[3] ^= 1;
+    return HG_OK;
+}
+
+int hg_launch_rain(hg_ctx* c, float time) {
+    SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
+    dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
+    RainArgs A{hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1), hg_total_live(c) ? hg_total(c, 1) : nullptr,
+               hg_cur(c, PL_ROCK, 0), hg_cur(c, PL_DIRT, 0), hg_cur(c, PL_WATER, 0), c->aux ? hg_total(c, 0) : nullptr};
+    k_rain<<<g, b, 0, c->stream>>>(d, c->rain, c->map, time, A);
+    HG_LAUNCH_CHECK(c);
+    c->ri[0] ^= 1;
+    return HG_OK;
+}

@@ -1,0 +1,141 @@
+// hg_internal.cuh — context object and device-side layout shared by the .cu files.
+//
+// Device layout: every field channel is one fp32 plane of
+// (rows + 2*HG_HALO_ROWS) x W elements, row-major, ghost rows first.  The nine
+// persistent planes (rock, dirt, water, fL, fR, fT, fB, sed_rock, sed_dirt) exist
+// twice (ping-pong sets 0/1) inside ONE arena allocation so a single CUDA IPC
+// handle exports a slab to its neighbours.  Each field keeps its own read index,
+// mirroring gl::Tex_pair (src/shaderprogram.cpp:51-82).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/hydrogen_b200.h"
+#include "hg_cell.cuh"
+
+enum HgPlane {
+    PL_ROCK = 0, PL_DIRT = 1, PL_WATER = 2,
+    PL_FL = 3, PL_FR = 4, PL_FT = 5, PL_FB = 6,
+    PL_SR = 7, PL_SD = 8,
+    HG_NPLANES = 9
+};
+// aux planes, allocated on first use of the PASSES schedule or particle mode
+enum HgAuxPlane {
+    AX_TOTAL0 = 0, AX_TOTAL1 = 1,                 // H.a, ping-pong with the heightmap
+    AX_V0 = 2,                                    // velocity / momentum: 4 channels x 2 sets
+    AX_TC = 10, AX_TD = 14,                       // thermal outflow, 4 channels each
+    HG_NAUX = 18
+};
+
+struct HgGeom {
+    int W, H;          // global map size
+    int row0, rows;    // slab: global rows [row0, row0+rows)
+    int pitch;         // floats per row (= W)
+    int rows_alloc;    // rows + 2*HG_HALO_ROWS
+    size_t plane_elems;
+};
+
+// Every rank's slab as seen from this process: arena base (both plane sets + flag page),
+// first owned row, owned rows.  n == 0 until hg_slab_connect*; entry `me` is this context.
+struct HgSlabTable {
+    float* arena[HG_MAX_SLABS];
+    int row0[HG_MAX_SLABS];
+    int rows[HG_MAX_SLABS];
+    int n, me;
+};
+
+// pointers to local row 0 of the ghost region (i.e. global row row0 - HG_HALO_ROWS)
+struct HgPlaneSet { float* p[HG_NPLANES]; };
+struct HgConstPlaneSet { const float* p[HG_NPLANES]; };
+
+struct hg_ctx {
+    int device;
+    int erosion_type;
+    int schedule;
+    HgGeom g;
+    uint32_t particle_count;
+    uint32_t erosion_steps;
+    hg_erosion_data erosion;
+    hg_rain_data rain;
+    hg_map_settings_data map;
+    HgStepParams sp;
+
+    float* arena;              // 2 * HG_NPLANES planes + flag page
+    size_t arena_bytes;
+    float* aux;                // HG_NAUX planes (lazy)
+    // read index per field group: 0 H, 1 F, 2 V, 3 S (Tex_pair::idx_read)
+    int ri[4];
+    hg_particle* particles;
+    uint32_t* lockmap;         // unused by the CUDA path (atomics replace the spin lock); kept for layout parity
+
+    cudaStream_t stream;
+    bool own_stream;
+    cudaEvent_t ev0, ev1;
+    uint64_t launches;
+    unsigned long long* d_counters;   // [0] far-fetch cells
+    float* staging;            // device staging for RGBA pack/unpack
+    size_t staging_elems;
+
+    // multi-GPU slabs (hg_slab.cu): every rank's arena, ordered by row0
+    HgSlabTable slabs;
+    bool slab_ipc[HG_MAX_SLABS];
+    uint32_t step_flag;        // halo generation counter
+    bool peers_connected;
+};
+
+void hg_set_error(const char* fmt, ...);
+
+#define HG_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            hg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return HG_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define HG_CHECK_CTX(ctx)                                   \
+    do {                                                    \
+        if (!(ctx)) { hg_set_error("null context"); return HG_ERR_INVALID; } \
+        cudaError_t _e = cudaSetDevice((ctx)->device);      \
+        if (_e != cudaSuccess) { hg_set_error("cudaSetDevice: %s", cudaGetErrorString(_e)); return HG_ERR_CUDA; } \
+    } while (0)
+
+#define HG_LAUNCH_CHECK(ctx)                                \
+    do {                                                    \
+        (ctx)->launches++;                                  \
+        cudaError_t _e = cudaGetLastError();                \
+        if (_e != cudaSuccess) { hg_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); return HG_ERR_CUDA; } \
+    } while (0)
+
+static inline float* hg_plane(hg_ctx* c, int set, int plane) {
+    return c->arena + ((size_t)set * HG_NPLANES + plane) * c->g.plane_elems;
+}
+static inline float* hg_aux_plane(hg_ctx* c, int idx) { return c->aux + (size_t)idx * c->g.plane_elems; }
+static inline int hg_field_of_plane(int plane) { return plane <= PL_WATER ? 0 : plane <= PL_FB ? 1 : 3; }
+// current read (rd=1) or write (rd=0) plane of the persistent state
+static inline float* hg_cur(hg_ctx* c, int plane, int rd) {
+    int f = hg_field_of_plane(plane);
+    int set = rd ? c->ri[f] : 1 - c->ri[f];
+    return hg_plane(c, set, plane);
+}
+static inline float* hg_total(hg_ctx* c, int rd) { return hg_aux_plane(c, rd ? AX_TOTAL0 + c->ri[0] : AX_TOTAL0 + 1 - c->ri[0]); }
+static inline float* hg_vel(hg_ctx* c, int ch, int rd) { return hg_aux_plane(c, AX_V0 + 4 * (rd ? c->ri[2] : 1 - c->ri[2]) + ch); }
+
+int hg_ensure_aux(hg_ctx* c);
+int hg_fill_total(hg_ctx* c);
+// the H.a planes are maintained only by the PASSES schedule and by particle mode
+static inline bool hg_total_live(const hg_ctx* c) { return c->aux && (c->schedule == HG_SCHEDULE_PASSES || c->erosion_type == HG_PARTICLES); }
+
+// implemented per file
+int hg_launch_passes_step(hg_ctx* c);
+int hg_launch_pass(hg_ctx* c, int pass);
+int hg_launch_fused_step(hg_ctx* c);
+int hg_launch_rain(hg_ctx* c, float time);
+int hg_launch_heightmap(hg_ctx* c);
+int hg_launch_particle_move(hg_ctx* c, float time, int should_rain);
+int hg_launch_particle_erode(hg_ctx* c);
+int hg_launch_thermal_smooth_particle(hg_ctx* c);
+int hg_slab_exchange(hg_ctx* c);     // push edge rows to neighbours + wait (no-op without peers)
+void hg_slab_disconnect(hg_ctx* c);

@@ -1,0 +1,212 @@
+// hg_slab.cu — row-slab halo exchange between GPUs over NVLink peer memory.
+//
+// The reference is single-GPU; this is new design for BASELINE configs 3
+// and 5.  Rank g owns global rows [row0, row0+rows) of all nine planes and keeps
+// HG_HALO_ROWS ghost rows on each side.  One fused step consumes 6 ghost rows (flux 1 +
+// thermal 2+2 + smooth 1; SURVEY.md §8a "dependency radii"), so ONE exchange per step
+// suffices: after its step kernel a rank stores its new edge rows straight into the two
+// neighbours' ghost rows through peer-mapped pointers (CUDA IPC between processes, plain
+// pointers inside one process) and then publishes the step number in a flag word of
+// EVERY rank.  The next step starts with a device-side wait until all ranks have
+// published that number.  No host round trip, no collective: the data path is two
+// nearest-neighbour stores plus n flag words.
+//
+// Why all ranks and not just the neighbours: the sediment back-trace is unbounded
+// (sediment_transport.glsl:27-28), so the fused kernel's far-fetch path may read the
+// PRE-step planes of any rank through its peer pointer.  That read is only safe while no
+// rank is a step ahead (it would be overwriting those planes) or behind (still writing
+// them); the all-rank flag wait is that guarantee.
+#include "hg_internal.cuh"
+
+namespace {
+
+struct PushArgs {
+    const float* src[HG_NPLANES];   // my planes (current read set), local row 0
+    float* dst[HG_NPLANES];         // neighbour's planes, same set
+    size_t src_off, dst_off;        // element offsets of the first row to copy
+    size_t n;                       // elements per plane (HG_HALO_ROWS * pitch)
+};
+
+// float4 copy of HG_HALO_ROWS rows x 9 planes into the neighbour's ghost rows
+__global__ void __launch_bounds__(256) k_halo_push(PushArgs A) {
+    int plane = blockIdx.y;
+    const float4* s = reinterpret_cast<const float4*>(A.src[plane] + A.src_off);
+    float4* d = reinterpret_cast<float4*>(A.dst[plane] + A.dst_off);
+    size_t n4 = A.n / 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+struct FlagArgs { unsigned* flag[HG_MAX_SLABS]; int n; };
+
+// after the pushes of this step, in stream order: write `gen` into my word on every rank
+__global__ void k_halo_signal(FlagArgs F, unsigned gen) {
+    __threadfence_system();
+    if ((int)threadIdx.x < F.n && F.flag[threadIdx.x]) *reinterpret_cast<volatile unsigned*>(F.flag[threadIdx.x]) = gen;
+    __threadfence_system();
+}
+// bounded spin until every rank's word in MY flag page reached `gen`; on timeout it records
+// an error instead of hanging the GPU
+__global__ void k_halo_wait(FlagArgs F, unsigned gen, unsigned long long* err) {
+    if ((int)threadIdx.x >= F.n || !F.flag[threadIdx.x]) return;
+    const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(F.flag[threadIdx.x]);
+    long long t0 = clock64();
+    const long long limit = 6000000000LL;   // ~3 s
+    while ((int)(*f - gen) < 0) {
+        if (clock64() - t0 > limit) { atomicAdd(err, 1ull); return; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+// flag word written by rank `from`, inside the flag page that follows the planes of `arena`
+inline unsigned* flag_ptr(float* arena, size_t plane_elems, int from) {
+    return reinterpret_cast<unsigned*>(arena + (size_t)2 * HG_NPLANES * plane_elems) + from * 32;   // 128 B apart
+}
+inline size_t plane_elems_of(const hg_ctx* c, int k) { return (size_t)(c->slabs.rows[k] + 2 * HG_HALO_ROWS) * c->g.pitch; }
+
+}  // namespace
+
+extern "C" int hg_slab_export_handle(hg_ctx* c, hg_slab_export* out) {
+    HG_CHECK_CTX(c);
+    if (!out) return HG_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    cudaIpcMemHandle_t h;
+    HG_CUDA(cudaIpcGetMemHandle(&h, c->arena));
+    static_assert(sizeof(h) <= HG_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(out->mem_handle, &h, sizeof(h));
+    out->arena_bytes = c->arena_bytes;
+    out->row0 = (uint32_t)c->g.row0; out->rows = (uint32_t)c->g.rows;
+    out->map_w = (uint32_t)c->g.W; out->map_h = (uint32_t)c->g.H;
+    out->device = c->device;
+    return HG_OK;
+}
+
+static int check_layout(hg_ctx* c, int n, int me, const int* row0, const int* rows, const int* w, const int* h) {
+    if (n < 1 || n > HG_MAX_SLABS || me < 0 || me >= n) { hg_set_error("bad slab table (n=%d, me=%d)", n, me); return HG_ERR_INVALID; }
+    int next = 0;
+    for (int k = 0; k < n; k++) {
+        if (w[k] != c->g.W || h[k] != c->g.H || row0[k] != next || rows[k] < HG_HALO_ROWS) {
+            hg_set_error("slab %d (rows [%d,%d) of %dx%d) does not tile a %dx%d map in order, or is thinner than the halo (%d rows)",
+                         k, row0[k], row0[k] + rows[k], w[k], h[k], c->g.W, c->g.H, HG_HALO_ROWS);
+            return HG_ERR_INVALID;
+        }
+        next += rows[k];
+    }
+    if (next != c->g.H || row0[me] != c->g.row0 || rows[me] != c->g.rows) { hg_set_error("slab table does not cover the map or entry %d is not this context", me); return HG_ERR_INVALID; }
+    return HG_OK;
+}
+
+extern "C" int hg_slab_connect(hg_ctx* c, const hg_slab_export* all, int n, int me) {
+    HG_CHECK_CTX(c);
+    if (!all) return HG_ERR_INVALID;
+    int row0[HG_MAX_SLABS], rows[HG_MAX_SLABS], w[HG_MAX_SLABS], h[HG_MAX_SLABS];
+    for (int k = 0; k < n && k < HG_MAX_SLABS; k++) { row0[k] = (int)all[k].row0; rows[k] = (int)all[k].rows; w[k] = (int)all[k].map_w; h[k] = (int)all[k].map_h; }
+    int rc = check_layout(c, n, me, row0, rows, w, h);
+    if (rc) return rc;
+    hg_slab_disconnect(c);
+    for (int k = 0; k < n; k++) {
+        c->slabs.row0[k] = row0[k]; c->slabs.rows[k] = rows[k];
+        if (k == me) { c->slabs.arena[k] = c->arena; c->slab_ipc[k] = false; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, all[k].mem_handle, sizeof(hd));
+        void* p = nullptr;
+        HG_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        c->slabs.arena[k] = static_cast<float*>(p);
+        c->slab_ipc[k] = true;
+    }
+    c->slabs.n = n; c->slabs.me = me;
+    c->peers_connected = n > 1;
+    return HG_OK;
+}
+
+extern "C" int hg_slab_connect_local(hg_ctx* c, hg_ctx* const* all, int n, int me) {
+    HG_CHECK_CTX(c);
+    if (!all) return HG_ERR_INVALID;
+    int row0[HG_MAX_SLABS], rows[HG_MAX_SLABS], w[HG_MAX_SLABS], h[HG_MAX_SLABS];
+    for (int k = 0; k < n && k < HG_MAX_SLABS; k++) {
+        if (!all[k]) { hg_set_error("null slab %d", k); return HG_ERR_INVALID; }
+        row0[k] = all[k]->g.row0; rows[k] = all[k]->g.rows; w[k] = all[k]->g.W; h[k] = all[k]->g.H;
+    }
+    int rc = check_layout(c, n, me, row0, rows, w, h);
+    if (rc) return rc;
+    if (all[me] != c) { hg_set_error("entry %d is not this context", me); return HG_ERR_INVALID; }
+    hg_slab_disconnect(c);
+    for (int k = 0; k < n; k++) {
+        if (all[k]->device != c->device) {
+            int can = 0;
+            HG_CUDA(cudaDeviceCanAccessPeer(&can, c->device, all[k]->device));
+            if (!can) { hg_set_error("device %d cannot access device %d", c->device, all[k]->device); return HG_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[k]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { hg_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return HG_ERR_CUDA; }
+            cudaGetLastError();
+        }
+        c->slabs.arena[k] = all[k]->arena;
+        c->slabs.row0[k] = row0[k]; c->slabs.rows[k] = rows[k];
+        c->slab_ipc[k] = false;
+    }
+    c->slabs.n = n; c->slabs.me = me;
+    c->peers_connected = n > 1;
+    return HG_OK;
+}
+
+void hg_slab_disconnect(hg_ctx* c) {
+    for (int k = 0; k < c->slabs.n; k++)
+        if (c->slab_ipc[k] && c->slabs.arena[k]) cudaIpcCloseMemHandle(c->slabs.arena[k]);
+    memset(&c->slabs, 0, sizeof(c->slabs));
+    memset(c->slab_ipc, 0, sizeof(c->slab_ipc));
+    c->peers_connected = false;
+}
+
+extern "C" int hg_slab_errors(hg_ctx* c, uint64_t* count) {
+    HG_CHECK_CTX(c);
+    unsigned long long v = 0;
+    HG_CUDA(cudaMemcpyAsync(&v, c->d_counters + 1, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (count) *count = v;
+    return HG_OK;
+}
+
+// After a fused step: push my new edge rows to both neighbours, publish the generation on
+// every rank, then make this stream wait until every rank has published it.
+int hg_slab_exchange(hg_ctx* c) {
+    if (!c->peers_connected) return HG_OK;
+    const HgSlabTable& T = c->slabs;
+    c->step_flag++;
+    const unsigned gen = c->step_flag;
+    const size_t rowsz = (size_t)c->g.pitch;
+    for (int s = 0; s < 2; s++) {
+        int nb = T.me + (s == 0 ? -1 : 1);
+        if (nb < 0 || nb >= T.n) continue;
+        PushArgs A;
+        size_t nb_elems = plane_elems_of(c, nb);
+        for (int p = 0; p < HG_NPLANES; p++) {
+            int set = c->ri[hg_field_of_plane(p)];
+            A.src[p] = hg_plane(c, set, p);
+            A.dst[p] = T.arena[nb] + ((size_t)set * HG_NPLANES + p) * nb_elems;
+        }
+        A.n = (size_t)HG_HALO_ROWS * rowsz;
+        if (s == 0) {   // my first owned rows -> lower neighbour's upper ghost rows
+            A.src_off = (size_t)HG_HALO_ROWS * rowsz;
+            A.dst_off = (size_t)(HG_HALO_ROWS + T.rows[nb]) * rowsz;
+        } else {        // my last owned rows -> upper neighbour's lower ghost rows
+            A.src_off = (size_t)c->g.rows * rowsz;
+            A.dst_off = 0;
+        }
+        size_t blocks = (A.n / 4 + 255) / 256;
+        dim3 grid((unsigned)(blocks < 64 ? blocks : 64), HG_NPLANES);
+        k_halo_push<<<grid, 256, 0, c->stream>>>(A);
+        HG_LAUNCH_CHECK(c);
+    }
+    FlagArgs S{}, Wt{};
+    S.n = Wt.n = T.n;
+    for (int k = 0; k < T.n; k++) {
+        if (k == T.me) continue;
+        S.flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);     // my word on rank k
+        Wt.flag[k] = flag_ptr(c->arena, c->g.plane_elems, k);             // rank k's word on me
+    }
+    k_halo_signal<<<1, 32, 0, c->stream>>>(S, gen);
+    HG_LAUNCH_CHECK(c);
+    k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, gen, c->d_counters + 1);
+    HG_LAUNCH_CHECK(c);
+    return HG_OK;
+}

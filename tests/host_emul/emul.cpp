@@ -1,0 +1,113 @@
+// emul.cpp — host build of the product's per-cell arithmetic (hydro_gen_b200/csrc/hg_cell.cuh,
+// hg_noise.cuh compiled as plain C++, no CUDA) driven by simple loops over SoA planes.
+// TEST INFRASTRUCTURE for `-m "not gpu"`: it checks, on a machine without a GPU, that the
+// device functions reproduce the oracle bit for bit.  It is not a CPU fallback: nothing in
+// the product links or loads it.
+#include <cstring>
+#include <vector>
+#include "../../hydro_gen_b200/csrc/hg_cell.cuh"
+#include "../../hydro_gen_b200/csrc/hg_noise.cuh"
+
+namespace {
+struct Dom { int W, H; };
+inline bool oob(const Dom& d, int x, int y) { return x < 0 || x > d.W - 1 || y < 0 || y > d.H - 1; }
+inline float ld(const float* p, const Dom& d, int x, int y, float o) { return oob(d, x, y) ? o : p[(size_t)y * d.W + x]; }
+}
+
+extern "C" {
+
+// planes: rock dirt water fL fR fT fB sr sd, each W*H, updated in place by one grid step
+// (the sequence of src/erosion.cpp:158-200).  Returns number of cells whose back-trace
+// footprint left the +-1 window (what the fused kernel's far-fetch path handles).
+long emul_grid_step(const hg_erosion_data* set, int W, int H, float* pl[9]) {
+    HgStepParams P = hg_make_step_params(*set);
+    Dom d{W, H};
+    size_t n = (size_t)W * H;
+    std::vector<float> a(n), u(n), v(n), vz(n), nw(n), nf[4], er(n), ed(n), esr(n), esd(n);
+    for (auto& f : nf) f.resize(n);
+    float *rock = pl[0], *dirt = pl[1], *water = pl[2], *sr = pl[7], *sd = pl[8];
+    for (size_t i = 0; i < n; i++) a[i] = rock[i] + dirt[i] + water[i];
+    // flux
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        size_t i = (size_t)y * W + x;
+        HgFluxOut o = hg_flux_cell(P, x, y, W, H, a[i], ld(a.data(), d, x - 1, y, HG_OOB_HEIGHT), ld(a.data(), d, x + 1, y, HG_OOB_HEIGHT),
+            ld(a.data(), d, x, y + 1, HG_OOB_HEIGHT), ld(a.data(), d, x, y - 1, HG_OOB_HEIGHT),
+            pl[3][i], pl[4][i], pl[5][i], pl[6][i],
+            ld(pl[4], d, x - 1, y, 0), ld(pl[3], d, x + 1, y, 0), ld(pl[6], d, x, y + 1, 0), ld(pl[5], d, x, y - 1, 0), water[i]);
+        nf[0][i] = o.fL; nf[1][i] = o.fR; nf[2][i] = o.fT; nf[3][i] = o.fB;
+        nw[i] = o.water; u[i] = o.u; v[i] = o.v; vz[i] = o.vz;
+    }
+    for (int k = 0; k < 4; k++) memcpy(pl[3 + k], nf[k].data(), n * 4);
+    // erosion
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        size_t i = (size_t)y * W + x;
+        HgEroOut e = hg_erosion_cell(P, rock[i], dirt[i], sr[i], sd[i], u[i], v[i], vz[i],
+            ld(rock, d, x + 1, y, 0), ld(dirt, d, x + 1, y, 0), ld(rock, d, x - 1, y, 0), ld(dirt, d, x - 1, y, 0),
+            ld(rock, d, x, y - 1, 0), ld(dirt, d, x, y - 1, 0), ld(rock, d, x, y + 1, 0), ld(dirt, d, x, y + 1, 0));
+        er[i] = e.rock; ed[i] = e.dirt; esr[i] = e.sr; esd[i] = e.sd;
+    }
+    // sediment transport + evaporation
+    long far = 0;
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        size_t i = (size_t)y * W + x;
+        HgBack b = hg_backtrace(P, x, y, W, H, u[i], v[i]);
+        int dx = b.px - x, dy = b.py - y;
+        if (!(dx >= -1 && dx <= 0 && dy >= -1 && dy <= 0)) far++;
+        sr[i] = hg_bilerp(ld(esr.data(), d, b.px, b.py, 0), ld(esr.data(), d, b.px + 1, b.py, 0),
+                          ld(esr.data(), d, b.px, b.py + 1, 0), ld(esr.data(), d, b.px + 1, b.py + 1, 0), b.sx, b.sy);
+        sd[i] = hg_bilerp(ld(esd.data(), d, b.px, b.py, 0), ld(esd.data(), d, b.px + 1, b.py, 0),
+                          ld(esd.data(), d, b.px, b.py + 1, 0), ld(esd.data(), d, b.px + 1, b.py + 1, 0), b.sx, b.sy);
+        water[i] = nw[i] * P.evap;
+    }
+    // thermal, layers 0 then 1
+    const int ox[8] = {-1, 1, 0, 0, -1, 1, -1, 1}, oy[8] = {0, 0, 1, -1, 1, 1, -1, -1};
+    std::vector<float> out[8], neg(n);
+    for (auto& o : out) o.resize(n);
+    for (int layer = 0; layer < 2; layer++) {
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            size_t i = (size_t)y * W + x;
+            float d_h[8], o8[8];
+            for (int k = 0; k < 8; k++) {
+                float dh = 0.0f;
+                dh += er[i] - ld(er.data(), d, x + ox[k], y + oy[k], HG_OOB_HEIGHT);
+                if (layer == 1) dh += ed[i] - ld(ed.data(), d, x + ox[k], y + oy[k], HG_OOB_HEIGHT);
+                d_h[k] = dh;
+            }
+            neg[i] = hg_thermal_outflow(P, layer, layer == 0 ? er[i] : ed[i], d_h, o8);
+            for (int k = 0; k < 8; k++) out[k][i] = o8[k];
+        }
+        std::vector<float>& tgt = layer == 0 ? er : ed;
+        std::vector<float> nt(n);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            size_t i = (size_t)y * W + x;
+            float delta = hg_thermal_delta(neg[i], ld(out[1].data(), d, x - 1, y, 0), ld(out[0].data(), d, x + 1, y, 0),
+                ld(out[3].data(), d, x, y + 1, 0), ld(out[2].data(), d, x, y - 1, 0),
+                ld(out[7].data(), d, x - 1, y + 1, 0), ld(out[6].data(), d, x + 1, y + 1, 0),
+                ld(out[5].data(), d, x - 1, y - 1, 0), ld(out[4].data(), d, x + 1, y - 1, 0));
+            nt[i] = tgt[i] + delta;
+        }
+        tgt.swap(nt);
+    }
+    // smoothing
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        size_t i = (size_t)y * W + x;
+        float r = er[i], g = ed[i];
+        if (!(x == 0 || y == 0 || x == W - 1 || y == H - 1))
+            hg_smooth_cell(P, r, g, er[i - 1], ed[i - 1], er[i + 1], ed[i + 1], er[i + W], ed[i + W], er[i - W], ed[i - W]);
+        rock[i] = r; dirt[i] = g;
+    }
+    return far;
+}
+
+void emul_heightmap(const hg_map_settings_data* cfg, int W, int H, float* rock, float* dirt) {
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) hg_heightmap_cell(*cfg, x, y, W, H, rock[(size_t)y * W + x], dirt[(size_t)y * W + x]);
+}
+
+void emul_rain(const hg_rain_data* set, const hg_map_settings_data* map_set, float time, int W, int H,
+               const float* rock, const float* dirt, float* water) {
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        size_t i = (size_t)y * W + x;
+        water[i] += hg_rain_cell(*set, *map_set, time, x, y, rock[i] + dirt[i] + water[i]);
+    }
+}
+}
