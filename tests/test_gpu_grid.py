@@ -1,0 +1,249 @@
+"""GPU parity tests of the grid erosion path, through the C ABI.
+
+The CUDA library is compiled -fmad=false and the oracle -ffp-contract=off, and both use
+include/hg_defined_math.h for atan/exp/sin, so the bar here is stronger than the north
+star's 1e-5: every field must match the oracle BIT FOR BIT.  The north-star tolerance is
+asserted as well (max_rel_err <= 1e-5) so the stated gate is visible in the test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from hydro_gen_b200 import Context, _lib
+from tests.util import DT_TIME, FIELDS, SEED, assert_bit_equal, copy_state, max_rel_err, wet_world
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # north star: per-field max relative error after 1 step
+
+
+@pytest.fixture(scope="module")
+def wet256():
+    w = wet_world(256, 300)
+    yield w
+    w.close()
+
+
+def _compare(ctx, ref, names, what):
+    for name in names:
+        got, want = ctx.download(FIELDS[name]), ref.get(FIELDS[name])
+        assert max_rel_err(got, want) <= TOL, f"{what}: {name} beyond the north-star tolerance"
+        assert_bit_equal(got, want, f"{what}: {name}")
+
+
+def test_heightmap_init_bit_exact(built):
+    """heightmap.glsl via hg_gen_heightmap vs the oracle (default map settings, injected seed)."""
+    for n, seed in ((256, SEED), (64, 77.25)):
+        ctx = Context(n)
+        m = ctx.get_map(); m.seed = seed; ctx.set_map(m)
+        ctx.gen_heightmap()
+        ref = oracle.World(n, seed=seed); ref.gen_heightmap()
+        _compare(ctx, ref, ("heightmap", "flux", "sediment"), f"init {n}")
+        ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("variant", ["uplift_terrace", "round_slope_warp2"])
+def test_heightmap_init_variants(built, variant):
+    """every branch of heightmap.glsl:85-131 (uplift/ridged sfbm, masks, terrace, 2-level warp)"""
+    n = 128
+    ctx = Context(n)
+    ref = oracle.World(n, seed=SEED)
+    m = ctx.get_map(); m.seed = SEED
+    if variant == "uplift_terrace":
+        m.uplift, m.terrace, m.terrace_scale = 1, 6, 0.5
+    else:
+        m.mask_round, m.mask_slope, m.domain_warp, m.mask_exp = 1, 1, 2, 0
+    ctx.set_map(m)
+    C.memmove(C.addressof(ref.map), C.addressof(m), C.sizeof(m))
+    ctx.gen_heightmap(); ref.gen_heightmap()
+    _compare(ctx, ref, ("heightmap",), variant)
+    ctx.close(); ref.close()
+
+
+def test_rain_bit_exact(built, wet256):
+    ctx = Context(256)
+    ctx.set_map(_lib.MapSettingsData.from_buffer_copy(bytes(wet256.map)))
+    copy_state(wet256, ctx)
+    ref = wet_world(256, 0)
+    for f in ("heightmap", "flux", "sediment"):
+        ref.set(FIELDS[f], wet256.get(FIELDS[f]))
+    for t in (0.123, 4.5):
+        ctx.dispatch_grid_rain(t)
+        ref.dispatch_grid_rain(t)
+    _compare(ctx, ref, ("heightmap",), "rain")
+    ctx.close(); ref.close()
+
+
+def _clone_oracle(src, n):
+    ref = oracle.World(n, seed=SEED)
+    for f in ("heightmap", "flux", "velocity", "sediment"):
+        ref.set(FIELDS[f], src.get(FIELDS[f]))
+    ref.rain.period = src.rain.period
+    ref.steps = src.steps
+    return ref
+
+
+def test_passes_each_dispatch_bit_exact(built, wet256):
+    """PASSES schedule: after every one of the reference's dispatches (erosion.cpp:158-200)
+    all materialised textures equal the oracle's, including V, TC, TD and H.a."""
+    ctx = Context(256)
+    ctx.set_schedule(_lib.SCHEDULE_PASSES)
+    copy_state(wet256, ctx, ("heightmap", "flux", "velocity", "sediment"))
+    ref = _clone_oracle(wet256, 256)
+    for p, names in ((oracle.PASS_FLUX, ("heightmap", "flux", "velocity")),
+                     (oracle.PASS_EROSION, ("heightmap", "sediment")),
+                     (oracle.PASS_SEDIMENT, ("heightmap", "sediment")),
+                     (oracle.PASS_THERMAL, ("heightmap", "thermal_c", "thermal_d")),
+                     (oracle.PASS_SMOOTH, ("heightmap",))):
+        ctx.dispatch_pass(p)
+        ref.run_pass(p)
+        _compare(ctx, ref, names, f"pass {p}")
+    ctx.close(); ref.close()
+
+
+def test_fused_one_step_bit_exact(built, wet256):
+    """The product path: one fused step == the oracle's 8-pass step, from a wet state in
+    which every branch is live (north-star gate (i))."""
+    ctx = Context(256)
+    copy_state(wet256, ctx)
+    ref = _clone_oracle(wet256, 256)
+    ctx.dispatch_grid(); ref.dispatch_grid()
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "fused step")
+    assert ctx.launch_count > 0
+    ctx.close(); ref.close()
+
+
+def test_fused_run_with_rain_and_far_fetch(built, wet256):
+    """48 main-loop iterations (rain every 16) stay bit-identical, and the far-fetch path
+    (back-trace leaving the +-1 window) is actually exercised."""
+    ctx = Context(256)
+    copy_state(wet256, ctx)
+    r = ctx.get_rain(); r.period = 16; ctx.set_rain(r)
+    ctx.set_map(_lib.MapSettingsData.from_buffer_copy(bytes(wet256.map)))
+    ctx.steps = wet256.steps
+    ref = _clone_oracle(wet256, 256)
+    ctx.far_fetch_count()
+    t0 = (wet256.steps + 1) * DT_TIME
+    ctx.run(48, t0, DT_TIME, True)
+    for k in range(48):
+        ref.step(np.float32(t0) + np.float32(k) * np.float32(DT_TIME))
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "48 steps")
+    assert ctx.far_fetch_count() > 0, "far-fetch path never taken: the test state is too tame"
+    assert ctx.steps == ref.steps
+    ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 8), (8, 40), (136, 24), (120, 264), (248, 72)])
+def test_fused_ragged_sizes(built, shape):
+    """Smallest legal map, non-square maps, widths around the strip width (116 owned columns)
+    and heights around the row-segment length: strip / segment edges and the map border."""
+    W, H = shape
+    ref = wet_world(H, 40, period=4, width=W)
+    ctx = Context(W, H)
+    src = _clone_like(ref, W, H)
+    copy_state(src, ctx)
+    for _ in range(3):
+        ctx.dispatch_grid(); src.dispatch_grid()
+    _compare(ctx, src, ("heightmap", "flux", "sediment"), f"{W}x{H}")
+    ctx.close(); ref.close(); src.close()
+
+
+def _clone_like(src, W, H):
+    ref = oracle.World(W, H, seed=SEED)
+    for f in ("heightmap", "flux", "velocity", "sediment"):
+        ref.set(FIELDS[f], src.get(FIELDS[f]))
+    return ref
+
+
+def test_fused_equals_passes_schedule(built, wet256):
+    """Both schedules of the library give the same bits (and can be switched between steps)."""
+    a, b = Context(256), Context(256)
+    b.set_schedule(_lib.SCHEDULE_PASSES)
+    copy_state(wet256, a); copy_state(wet256, b, ("heightmap", "flux", "velocity", "sediment"))
+    for _ in range(4):
+        a.dispatch_grid(); b.dispatch_grid()
+    for name in ("heightmap", "flux", "sediment"):
+        assert_bit_equal(a.download(FIELDS[name]), b.download(FIELDS[name]), f"fused vs passes: {name}")
+    a.set_schedule(_lib.SCHEDULE_PASSES)
+    a.dispatch_grid(); b.dispatch_grid()
+    assert_bit_equal(a.download(0), b.download(0), "after switching schedule")
+    a.close(); b.close()
+
+
+def test_dry_default_config(built):
+    """BASELINE config 1 as the reference runs it: period 512, so 60 steps never rain and
+    only thermal + smoothing act."""
+    n = 256
+    ctx = Context(n)
+    m = ctx.get_map(); m.seed = SEED; ctx.set_map(m)
+    ctx.gen_heightmap()
+    ctx.run(60, DT_TIME, DT_TIME, True)
+    ref = oracle.World(n, seed=SEED); ref.gen_heightmap()
+    for s in range(1, 61):
+        ref.step(s * DT_TIME)
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "dry 60 steps")
+    assert ctx.download(0)[..., 2].max() == 0.0
+    ctx.close(); ref.close()
+
+
+def test_steep_terrain_thermal_marks(built):
+    """Talus angles lowered so thermal slippage marks many neighbours (atan path, sharpness,
+    bk division) in both layers; dry."""
+    n = 128
+    ref = oracle.World(n, seed=SEED); ref.gen_heightmap()
+    H = ref.get(0)
+    rng = np.random.default_rng(5)
+    H[..., 0] += rng.random((n, n), dtype=np.float32) * 6.0
+    H[..., 1] += rng.random((n, n), dtype=np.float32) * 2.0
+    H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]
+    ref.set(0, H)
+    ref.erosion.Kalpha[0], ref.erosion.Kalpha[1] = 0.9, 0.3
+    ctx = Context(n)
+    ctx.set_erosion(_lib.ErosionData.from_buffer_copy(bytes(ref.erosion)))
+    copy_state(ref, ctx)
+    for _ in range(5):
+        ctx.dispatch_grid(); ref.dispatch_grid()
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "steep thermal")
+    ctx.close(); ref.close()
+
+
+def test_exhausted_dirt_layer(built, wet256):
+    """Thin dirt + aggressive dissolving: the 'layer went negative -> continue into rock'
+    branch of hydro_erosion.glsl:68-77."""
+    n = 256
+    ref = _clone_oracle(wet256, n)
+    H = ref.get(0); H[..., 1] = 1e-4; H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]; ref.set(0, H)
+    ref.erosion.Ks[1] = 50.0; ref.erosion.Kc = 5.0
+    ctx = Context(n)
+    ctx.set_erosion(_lib.ErosionData.from_buffer_copy(bytes(ref.erosion)))
+    copy_state(ref, ctx)
+    for _ in range(3):
+        ctx.dispatch_grid(); ref.dispatch_grid()
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "exhausted dirt")
+    ctx.close(); ref.close()
+
+
+def test_errors_are_loud(built):
+    L = _lib.load()
+    assert not L.hg_create(100, 100, 0, 0, 0) and b"multiple of 8" in L.hg_last_error()
+    assert not L.hg_create(64, 64, 0, 1, 0)      # particle mode without droplets
+    ctx = Context(64)
+    with pytest.raises(_lib.HydrogenError):
+        ctx.download(_lib.FIELD_VELOCITY)        # not materialised by the fused schedule
+    with pytest.raises(_lib.HydrogenError):
+        ctx.dispatch_particle(0.0)
+    with pytest.raises(_lib.HydrogenError):
+        ctx.dispatch_pass(0)
+    ctx.close()
+
+
+def test_mass_and_roundtrip(built, wet256):
+    ctx = Context(256)
+    copy_state(wet256, ctx)
+    H, S = wet256.get(0), wet256.get(3)
+    want = np.array([H[..., 0].sum(dtype=np.float64), H[..., 1].sum(dtype=np.float64), H[..., 2].sum(dtype=np.float64),
+                     S[..., 0].sum(dtype=np.float64), S[..., 1].sum(dtype=np.float64)])
+    np.testing.assert_allclose(ctx.mass(), want, rtol=1e-12)
+    assert_bit_equal(ctx.download(0), H, "upload/download round trip")
+    ctx.close()
