@@ -29,6 +29,7 @@ static void free_ctx(hg_ctx* c) {
     if (c->lockmap) cudaFree(c->lockmap);
     if (c->staging) cudaFree(c->staging);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->far_list) cudaFree(c->far_list);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -66,8 +67,8 @@ static int create_impl(hg_ctx* c) {
     c->arena_bytes = (size_t)2 * HG_NPLANES * c->g.plane_elems * sizeof(float) + 4096;
     HG_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
     HG_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
-    HG_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
-    HG_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    HG_CUDA(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
+    HG_CUDA(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
     if (c->particle_count) {
         // gl::gen_buffer(particle_buffer, particle_count * sizeof(Particle)), state.cpp:28-30; zeroed (hazard 6)
         HG_CUDA(cudaMalloc(&c->particles, (size_t)c->particle_count * sizeof(hg_particle)));

@@ -73,7 +73,10 @@ struct hg_ctx {
     bool own_stream;
     cudaEvent_t ev0, ev1;
     uint64_t launches;
-    unsigned long long* d_counters;   // [0] far-fetch cells
+    // 16 words: [0] far-fetch cells (total), [1] halo/far errors, [2..6] mass (fp64), [8],[9] per-step far counters
+    unsigned long long* d_counters;
+    unsigned* far_list;        // cells whose back-trace left the on-chip window this step (lazy)
+    int far_parity;
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
 

@@ -1,0 +1,139 @@
+"""CPU tests (no GPU): the product's device functions, compiled for the host by
+tests/host_emul, must reproduce the oracle bit for bit; the defined-math header must
+agree with libm; the monotonicity that the thermal marking threshold relies on holds."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from hydro_gen_b200 import _lib as hl
+from tests.util import DT_TIME, FIELDS, SEED, assert_bit_equal, wet_world
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "host_emul")], check=True)
+    E = C.CDLL(os.path.join(HERE, "host_emul", "libhg_emul.so"))
+    E.emul_grid_step.restype = C.c_long
+    return E
+
+
+def planes_of(w):
+    H, F, S = w.get(0), w.get(1), w.get(3)
+    return [np.ascontiguousarray(a) for a in (H[..., 0], H[..., 1], H[..., 2], F[..., 0], F[..., 1], F[..., 2], F[..., 3], S[..., 0], S[..., 1])]
+
+
+def emul_step(E, w, pl):
+    arr = (C.c_void_p * 9)(*[p.ctypes.data for p in pl])
+    er = hl.ErosionData.from_buffer_copy(bytes(w.erosion))
+    return E.emul_grid_step(C.byref(er), w.W, w.H, arr)
+
+
+def test_device_cell_math_matches_oracle_wet(emul):
+    """flux, erosion, sediment gather, thermal x2, smoothing and rain of hg_cell.cuh /
+    hg_noise.cuh vs the oracle over 24 wet steps (rain every 16) at 192x128."""
+    w = wet_world(128, 200, width=192)
+    mp = hl.MapSettingsData.from_buffer_copy(bytes(w.map))
+    far = 0
+    for _ in range(24):
+        pl = planes_of(w)
+        t = (w.steps + 1) * DT_TIME
+        if (w.steps + 1) % 16 == 0:
+            rn = hl.RainData.from_buffer_copy(bytes(w.rain))
+            emul.emul_rain(C.byref(rn), C.byref(mp), C.c_float(t), w.W, w.H, pl[0].ctypes.data_as(C.c_void_p),
+                           pl[1].ctypes.data_as(C.c_void_p), pl[2].ctypes.data_as(C.c_void_p))
+        far += emul_step(emul, w, pl)
+        w.step(t)
+        for got, want, name in zip(pl, planes_of(w), "rock dirt water fL fR fT fB sed_r sed_d".split()):
+            assert_bit_equal(got, want, name)
+    assert far > 0   # the state exercises back-traces beyond +-1 cell
+    w.close()
+
+
+def test_device_thermal_marking_matches_oracle_steep(emul):
+    """Lowered talus angles + roughened terrain: many marked neighbours in both layers, so the
+    threshold form of the marking test and the single-atan sharpness are exercised."""
+    n = 96
+    w = oracle.World(n, seed=SEED); w.gen_heightmap()
+    H = w.get(0)
+    rng = np.random.default_rng(3)
+    H[..., 0] += rng.random((n, n), dtype=np.float32) * 6
+    H[..., 1] += rng.random((n, n), dtype=np.float32) * 2
+    H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]
+    w.set(0, H)
+    for ka in ((0.9, 0.3), (1.3, 0.6), (0.05, 1.55), (-0.1, 2.0)):
+        w.erosion.Kalpha[0], w.erosion.Kalpha[1] = ka
+        for _ in range(3):
+            pl = planes_of(w)
+            emul_step(emul, w, pl)
+            w.dispatch_grid()
+            for got, want, name in zip(pl, planes_of(w), "rock dirt water fL fR fT fB sed_r sed_d".split()):
+                assert_bit_equal(got, want, f"Kalpha={ka}: {name}")
+    w.close()
+
+
+def test_device_heightmap_matches_oracle(emul):
+    for seed, variant in ((SEED, {}), (7.5, {"uplift": 1, "terrace": 5}), (99.0, {"mask_round": 1, "mask_slope": 1, "domain_warp": 2, "mask_exp": 0})):
+        n = 96
+        w = oracle.World(n, seed=seed)
+        for k, v in variant.items():
+            setattr(w.map, k, v)
+        w.gen_heightmap()
+        mp = hl.MapSettingsData.from_buffer_copy(bytes(w.map))
+        rock = np.zeros((n, n), np.float32); dirt = np.zeros((n, n), np.float32)
+        emul.emul_heightmap(C.byref(mp), n, n, rock.ctypes.data_as(C.c_void_p), dirt.ctypes.data_as(C.c_void_p))
+        H = w.get(0)
+        assert_bit_equal(rock, H[..., 0], f"rock {variant}")
+        assert_bit_equal(dirt, H[..., 1], f"dirt {variant}")
+        w.close()
+
+
+def _ulp_diff(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def test_defined_math_close_to_libm():
+    L = oracle.lib()
+    xs = np.concatenate([np.geomspace(1e-6, 1e6, 4000), np.linspace(0.3, 3.0, 4000)]).astype(np.float32)
+    at = np.array([L.orc_atanf(float(x)) for x in xs], np.float32)
+    assert _ulp_diff(at, np.arctan(xs.astype(np.float64)).astype(np.float32)).max() <= 4
+    xe = np.linspace(-5, 5, 4001).astype(np.float32)
+    ex = np.array([L.orc_expf(float(x)) for x in xe], np.float32)
+    assert _ulp_diff(ex, np.exp(xe.astype(np.float64)).astype(np.float32)).max() <= 4
+    xsn = np.concatenate([np.linspace(-20, 20, 4001), np.linspace(1e3, 4.3e5, 4001)]).astype(np.float32)
+    sn = np.array([L.orc_sinf(float(x)) for x in xsn], np.float32)
+    assert np.abs(sn - np.sin(xsn.astype(np.float64))).max() <= 3e-7
+
+
+def test_atan_monotone_where_thresholds_live():
+    """The exhaustive proof is scripts/check_atan_monotone.c (all 2^31 positive floats, ~1 min);
+    here: every float in windows around the range-reduction breakpoints and around tan(Kalpha)
+    for the default talus angles."""
+    L = oracle.lib()
+    for centre in (0.4142135623730950, 2.414213562373095, math.tan(0.6), math.tan(1.3), 1.0, 1e-3, 50.0):
+        c = np.float32(centre).view(np.uint32)
+        u = np.arange(int(c) - 3000, int(c) + 3000, dtype=np.uint32)
+        y = np.array([L.orc_atanf(float(v)) for v in u.view(np.float32)], np.float32)
+        assert np.all(np.diff(y) >= 0), centre
+
+
+def test_struct_layouts_match_the_reference():
+    """offsets of glsl/bindings.glsl:39-111"""
+    E, M = hl.ErosionData, hl.MapSettingsData
+    want = {"particle_count": 0, "Kc": 4, "Kalpha": 8, "Kconv": 16, "Ks": 24, "Kd": 32, "Ke": 40, "ENERGY_KEPT": 44,
+            "Kspeed": 48, "G": 56, "d_t": 60, "density": 64, "init_volume": 68, "friction": 72, "inertia": 76,
+            "min_volume": 80, "min_velocity": 84, "ttl": 88}
+    for k, off in want.items():
+        assert getattr(E, k).offset == off, k
+    assert C.sizeof(E) == 96 and C.sizeof(hl.RainData) == 20 and C.sizeof(M) == 96
+    assert M.hmap_dims.offset == 8 and M.seed.offset == 24 and M.octaves.offset == 44 and M.domain_warp.offset == 76
+    assert M.terrace_scale.offset == 88
+    assert oracle.PARTICLE_DTYPE.fields["sediment"][1] == 32 and oracle.PARTICLE_DTYPE.fields["to_kill"][1] == 40
