@@ -169,6 +169,9 @@ class Context:
     def timer_stop(self):
         ms = C.c_float(); check(self.L.hg_timer_stop(self.h, C.byref(ms))); return ms.value
 
+    def profile_fused(self, n_steps):
+        ms = C.c_float(); check(self.L.hg_profile_fused(self.h, int(n_steps), C.byref(ms))); return ms.value
+
     @property
     def launch_count(self):
         return int(self.L.hg_launch_count(self.h))

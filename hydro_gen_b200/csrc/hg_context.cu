@@ -408,6 +408,33 @@ extern "C" int hg_dispatch_grid(hg_ctx* c) {
     return hg_slab_exchange(c);
 }
 
+// Average duration of the fused step kernel alone (CUDA events around that one launch), over
+// n_steps real steps: advances the simulation like hg_dispatch_grid.  Blocking.
+extern "C" int hg_profile_fused(hg_ctx* c, uint32_t n_steps, float* avg_kernel_ms) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_GRID || c->schedule != HG_SCHEDULE_FUSED || !n_steps) { hg_set_error("hg_profile_fused needs a grid context on the FUSED schedule"); return HG_ERR_STATE; }
+    cudaEvent_t e0, e1;
+    HG_CUDA(cudaEventCreate(&e0));
+    HG_CUDA(cudaEventCreate(&e1));
+    double total = 0.0;
+    int rc = HG_OK;
+    for (uint32_t k = 0; k < n_steps && rc == HG_OK; k++) {
+        c->prof_ev0 = e0; c->prof_ev1 = e1;
+        rc = hg_launch_fused_step(c);
+        c->prof_ev0 = c->prof_ev1 = nullptr;
+        if (rc == HG_OK) rc = hg_slab_exchange(c);
+        if (rc == HG_OK && cudaEventSynchronize(e1) == cudaSuccess) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            total += ms;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (avg_kernel_ms) *avg_kernel_ms = (float)(total / n_steps);
+    return rc;
+}
+
 extern "C" int hg_dispatch_pass(hg_ctx* c, int pass) {
     HG_CHECK_CTX(c);
     if (c->schedule != HG_SCHEDULE_PASSES) { hg_set_error("hg_dispatch_pass needs HG_SCHEDULE_PASSES"); return HG_ERR_STATE; }

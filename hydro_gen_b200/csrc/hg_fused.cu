@@ -428,8 +428,10 @@ int hg_launch_fused_step(hg_ctx* c) {
     int nseg = (c->g.rows + seg - 1) / seg;
     size_t smem = ((size_t)R_TOTAL * NT + 2) * sizeof(float);
     static_assert(((size_t)R_TOTAL * NT + 2) * sizeof(float) <= 48 * 1024, "raise the dynamic shared memory limit for larger CTAs");
+    if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
     k_fused_step<NT, 4><<<A.nstrips * nseg, NT, smem, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);
+    if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);
     for (int f = 0; f < 4; f++) if (f != 2) c->ri[f] ^= 1;   // H, F, S flip once per fused step; V is not stored

@@ -72,6 +72,7 @@ struct hg_ctx {
     cudaStream_t stream;
     bool own_stream;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t prof_ev0, prof_ev1;   // set only inside hg_profile_fused
     uint64_t launches;
     // 16 words: [0] far-fetch cells (total), [1] halo/far errors, [2..6] mass (fp64), [8],[9] per-step far counters
     unsigned long long* d_counters;

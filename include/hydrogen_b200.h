@@ -131,6 +131,9 @@ void* hg_get_stream(hg_ctx* ctx);
 /* CUDA-event timing on the handle's stream: start, enqueue work, stop (blocking), ms. */
 int hg_timer_start(hg_ctx* ctx);
 int hg_timer_stop(hg_ctx* ctx, float* elapsed_ms);
+/* Average duration of the fused step kernel alone over n_steps real steps (CUDA events around
+ * that one launch on the handle's stream); the roofline figure of bench.py.  Blocking. */
+int hg_profile_fused(hg_ctx* ctx, uint32_t n_steps, float* avg_kernel_ms);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 uint64_t hg_launch_count(hg_ctx* ctx);
 /* Cells whose sediment back-trace left the on-chip window and took the far-fetch path,
