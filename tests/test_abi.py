@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: libhydrogen_b200.so loads without a GPU, exports every
+symbol include/hydrogen_b200.h declares, fails loudly (no CPU fallback) when no device is
+present, and the header compiles as plain C."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hydrogen_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = declared_functions()
+    assert len(names) >= 40, names
+    missing = [n for n in names if not hasattr(built, n)]
+    assert not missing, f"declared in hydrogen_b200.h but not exported: {missing}"
+
+
+def test_header_is_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "hydrogen_b200.h"\nint main(void){hg_erosion_data e = hg_default_erosion(0,0); return e.ttl != 0;}\n')
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device hg_create must fail with a message; with one it must work."""
+    import torch
+    h = built.hg_create(64, 64, 0, 0, 0)
+    if torch.cuda.is_available():
+        assert h
+        built.hg_destroy(h)
+    else:
+        assert not h
+        assert b"no CPU fallback" in built.hg_last_error()
+
+
+def test_bad_arguments_are_rejected_before_any_device_work(built):
+    assert not built.hg_create(60, 64, 0, 0, 0)              # not a multiple of 8 (erosion.cpp:96-97)
+    assert b"multiple of 8" in built.hg_last_error()
+    assert not built.hg_create(64, 64, 0, 7, 0)
+    assert b"erosion type" in built.hg_last_error()
+    assert not built.hg_create(64, 64, 0, 1, 0)              # particle mode without droplets
+    assert built.hg_version().startswith(b"hydrogen_b200")
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under hydro_gen_b200/ may reference it"""
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "hydro_gen_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                t = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|hg_oracle|oracle/", t, flags=re.M):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
