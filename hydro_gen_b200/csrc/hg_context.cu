@@ -2,6 +2,7 @@
 // field transfer in the reference's RGBA32F texture format, the per-step dispatch
 // schedule of src/erosion.cpp:76-200 and the main-loop rule of src/main.cpp:310-324.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <new>
 #include "hg_internal.cuh"
 
@@ -108,6 +109,9 @@ extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0,
     c->erosion = hg_default_erosion(erosion_type == HG_PARTICLES, particle_count);
     c->rain = hg_default_rain();
     c->map = hg_default_map(0.0f);
+    c->tune_variant = -1;
+    if (const char* e = getenv("HG_FUSED_SEG")) c->tune_seg = atoi(e);   // tuning aids
+    if (const char* e = getenv("HG_FUSED_VARIANT")) c->tune_variant = atoi(e);
     refresh_params(c);
     if (create_impl(c) != HG_OK) { free_ctx(c); return nullptr; }
     return c;

@@ -1,0 +1,351 @@
+// hg_fused_body.cuh — one row iteration of the fused grid erosion step, for one thread.
+//
+// Erosion::dispatch_grid (src/erosion.cpp:158-200: flux, erosion, sediment transport,
+// thermal x2 layers, smoothing) as a row-marching software pipeline.  A CTA of NT threads
+// owns a strip of NT-12 columns (6 halo columns each side, recomputed) and a segment of
+// rows; thread t holds column x0-6+t and marches in +y.  At iteration i every stage works
+// on its own lagged row:
+//
+//   L(i)    raw row i arrives (prefetched one iteration earlier); H.a = (r+g)+b
+//   A(i-1)  hydro_flux + hydro_erosion (+ evaporation)  -> F', water' to HBM; rockE, dirtE, S', u, v
+//   B(i-3)  sediment back-trace + bilinear gather of S' -> sediment' to HBM
+//   C(i-3)  thermal outflow, layer 0 (rock)             -> 8 outflows
+//   D(i-5)  thermal transport, layer 0                  -> rock1
+//   E(i-7)  thermal outflow, layer 1 (rock1 + dirtE)    -> 8 outflows
+//   F(i-9)  thermal transport, layer 1                  -> dirt2
+//   G(i-11) smoothing                                   -> rock', dirt' to HBM
+//
+// A thread keeps its own column's history in registers (HgCol); values of the x+-1
+// columns come through shared-memory row rings written at least one iteration earlier, so
+// ONE barrier per row is enough and the seven stages of an iteration are independent
+// instruction streams.  Ring rows are indexed by (absolute row mod N), N a power of two.
+// FREE=true is the steady state: every stage's row lies inside its active range and
+// strictly inside the map in y, so no range or y-border test is left; pipeline fill/drain
+// and the rows next to the map border use FREE=false, which tests everything.  The
+// steady-state body must stay inside the 32 KB L1.5 instruction cache: a 6x unrolled
+// version with compile-time ring slots executed 35 % fewer instructions and ran slower
+// (profiles/r01b: no_instruction stalls 0.3 -> 2.6 per issue).
+//
+// Exchanges are packed so one LDS/STS moves what a neighbour needs:
+//   XQ  float4 (H.a, rock, dirt, fR)   XL float fL          raw row            N=2
+//   RE  float  rockE                                        after stage A      N=2
+//   DE  float  dirtE (own column only, A -> D)                                 N=8
+//   SS  float2 (S'.rock, S'.dirt)                           after stage A      N=4
+//   OxR float4 (R, RT, RB, -)  OxL float4 (L, LT, LB, -)    thermal outflow    N=2, per layer
+//   R1D float2 (rock1, dirtE)                               after stage D      N=2
+//   G2  float2 (rock1, dirt2)                               after stage F      N=4
+//
+// This header is plain C++ apart from the HGF_* macros, so tests/host_emul runs the very
+// same body thread by thread on the CPU (-m "not gpu") against the oracle.
+#pragma once
+#include "hg_cell.cuh"
+
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+#define HGF_LDG(p) __ldg(p)
+#define HGF_ATOMIC_INC64(p) atomicAdd((p), 1ull)
+#else
+#define HGF_LDG(p) (*(p))
+#define HGF_ATOMIC_INC64(p) ((*(p))++)
+#endif
+
+constexpr int HGF_HX = 6;        // halo columns per side
+constexpr int HGF_LAG_G = 11;    // rows between L and G
+constexpr int HGF_NPL = 9;       // rock dirt water fL fR fT fB sr sd (HgPlane order)
+
+struct HgF4 { float x, y, z, w; };
+struct HgF2 { float x, y; };
+#if defined(__CUDACC__)
+static_assert(sizeof(HgF4) == 16 && sizeof(HgF2) == 8, "packed ring elements");
+#endif
+
+// Ring offsets in floats inside the CTA's shared block; every ring row has NT+2 elements
+// (one pad element each side so tid-1 / tid+1 of the edge threads stay inside).
+template <int NT> struct HgRings {
+    static constexpr int E = NT + 2;
+    static constexpr int XQ = 0;                    // float4 [2][E]
+    static constexpr int O0R = XQ + 2 * E * 4;      // float4 [2][E]
+    static constexpr int O0L = O0R + 2 * E * 4;
+    static constexpr int O1R = O0L + 2 * E * 4;
+    static constexpr int O1L = O1R + 2 * E * 4;
+    static constexpr int SS = O1L + 2 * E * 4;      // float2 [4][E]
+    static constexpr int R1D = SS + 4 * E * 2;      // float2 [2][E]
+    static constexpr int G2 = R1D + 2 * E * 2;      // float2 [4][E]
+    static constexpr int XL = G2 + 4 * E * 2;       // float  [2][E]
+    static constexpr int RE = XL + 2 * E;           // float  [2][E]
+    static constexpr int DE = RE + 2 * E;           // float  [8][E]
+    static constexpr int TOTAL = DE + 8 * E;        // 72 * E floats
+};
+
+struct HgFusedK {
+    const float* src[HGF_NPL];
+    float* dst[HGF_NPL];
+    int W, H, row0, rows, pitch;
+    int seg, nstrips;
+    unsigned* far_list;                  // local linear cell indices (row - row0) * W + x
+    unsigned long long* far_count;       // this step's counter
+    HgStepParams P;
+};
+
+// per-thread rolling state (one column)
+struct HgCol {
+    float rk0, rk1, rk2, dt0, dt1, dt2;          // rock, dirt rows i-2, i-1, i
+    float at0, at1, at2;                         // H.a
+    float w1, w2;                                // water rows i-1, i
+    float f1L, f1R, f1T, f1B, f2L, f2R, f2T, f2B, f0T;
+    float s1r, s1d, s2r, s2d;
+    float u_d1, v_d1, u_d2, v_d2;                // velocity delayed 1, 2 iterations
+    float e00, e01, e02, e10, e11, e12, e20, e21, e22;   // rockE rows i-4..i-2, columns x-1..x+1
+    float so0_d1, so0_d2, T0_d1, T0_d2, T0_d3, B0_d1;
+    float nR0_d1, nL0_d1, nRT0_d1, nRT0_d2, nLT0_d1, nLT0_d2;
+    float p00, p01, p02, p10, p11, p12, p20, p21, p22;   // rock1 rows i-8..i-6
+    float q00, q01, q02, q10, q11, q12, q20, q21, q22;   // dirtE rows i-8..i-6
+    float so1_d1, so1_d2, T1_d1, T1_d2, T1_d3, B1_d1;
+    float nR1_d1, nL1_d1, nRT1_d1, nRT1_d2, nLT1_d1, nLT1_d2;
+    float g_r0, g_r1, g_r2, g_d0, g_d1, g_d2;    // own column of (rock1, dirt2) rows i-12..i-10
+    float pf[HGF_NPL];                           // raw row i+1 in flight
+};
+
+HG_FN void hg_col_init(HgCol& c) {
+    float* f = reinterpret_cast<float*>(&c);
+    for (int k = 0; k < (int)(sizeof(HgCol) / sizeof(float)); k++) f[k] = 0.0f;
+    c.at0 = c.at1 = c.at2 = HG_OOB_HEIGHT;
+}
+
+// One iteration.  sm: the CTA's ring block; tid: thread index; x: global column of this
+// thread; xin/owned: column inside the map / inside the strip proper; gy0, gy1: the CTA's
+// row segment; off: element offset of (row i, column x) inside a plane.
+// FREE: see the header.
+template <int NT, bool FREE>
+HG_FN void hg_fused_iter(HgCol& c, float* sm, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
+                         const int gy0, const int gy1, const int i, const unsigned off) {
+    typedef HgRings<NT> R;
+    const HgStepParams& P = K.P;
+    const int W = K.W, H = K.H;
+    const unsigned pitch = (unsigned)K.pitch;
+    HgF4* const f4 = reinterpret_cast<HgF4*>(sm);
+    HgF2* const f2 = reinterpret_cast<HgF2*>(sm);
+    const int e = tid + 1;   // element index inside a ring row
+    // slot of absolute row (i - k) in a ring of n rows
+#define SLOT(k, n) ((i - (k)) & ((n) - 1))
+#define F4(ring, slot, el) f4[(ring) / 4 + (slot) * R::E + (el)]
+#define F2(ring, slot, el) f2[(ring) / 2 + (slot) * R::E + (el)]
+#define F1(ring, slot, el) sm[(ring) + (slot) * R::E + (el)]
+
+    // ------------------------------------------------------------ L(i)
+    c.rk0 = c.rk1; c.rk1 = c.rk2; c.dt0 = c.dt1; c.dt1 = c.dt2; c.at0 = c.at1; c.at1 = c.at2; c.w1 = c.w2;
+    c.f0T = c.f1T; c.f1L = c.f2L; c.f1R = c.f2R; c.f1T = c.f2T; c.f1B = c.f2B; c.s1r = c.s2r; c.s1d = c.s2d;
+    c.rk2 = c.pf[0]; c.dt2 = c.pf[1]; c.w2 = c.pf[2];
+    c.f2L = c.pf[3]; c.f2R = c.pf[4]; c.f2T = c.pf[5]; c.f2B = c.pf[6];
+    c.s2r = c.pf[7]; c.s2d = c.pf[8];
+    c.at2 = (xin && (FREE || (i >= 0 && i < H))) ? c.rk2 + c.dt2 + c.w2 : HG_OOB_HEIGHT;
+    {
+        HgF4 q; q.x = c.at2; q.y = c.rk2; q.z = c.dt2; q.w = c.f2R;
+        F4(R::XQ, SLOT(0, 2), e) = q;
+        F1(R::XL, SLOT(0, 2), e) = c.f2L;
+    }
+    // prefetch raw row i+1 (consumed next iteration)
+    {
+        const int gy = i + 1;
+        const bool ld = xin && (FREE || (gy >= 0 && gy < H && gy < gy1 + HGF_HX));
+        const unsigned noff = off + pitch;
+#pragma unroll
+        for (int p = 0; p < HGF_NPL; p++) c.pf[p] = ld ? HGF_LDG(K.src[p] + noff) : 0.0f;
+    }
+
+    // ------------------------------------------------------------ A(i-1)
+    float u_new = 0.0f, v_new = 0.0f;
+    {
+        const int ya = i - 1;
+        if (FREE || (ya >= gy0 - 5 && ya < gy1 + 5)) {
+            const bool in = xin && (FREE || (ya >= 0 && ya < H));
+            const HgF4 ql = F4(R::XQ, SLOT(1, 2), e - 1);     // left neighbour: H.a, rock, dirt, fR
+            const HgF4 qr = F4(R::XQ, SLOT(1, 2), e + 1);     // right neighbour: H.a, rock, dirt
+            const float inR = F1(R::XL, SLOT(1, 2), e + 1);   // right neighbour's fL
+            // FREE rows are strictly inside the map in y: y = 1, H = 4 folds the y-border tests away
+            HgFluxOut o = hg_flux_cell(P, x, FREE ? 1 : ya, W, FREE ? 4 : H, c.at1, ql.x, qr.x, c.at2, c.at0,
+                                       c.f1L, c.f1R, c.f1T, c.f1B, ql.w, inR, c.f2B, c.f0T, c.w1);
+            HgEroOut er = hg_erosion_cell(P, c.rk1, c.dt1, c.s1r, c.s1d, o.u, o.v, o.vz,
+                                          qr.y, qr.z, ql.y, ql.z, c.rk0, c.dt0, c.rk2, c.dt2);
+            u_new = o.u; v_new = o.v;
+            if (owned && in && (FREE || (ya >= gy0 && ya < gy1))) {
+                const unsigned idx = off - pitch;
+                K.dst[3][idx] = o.fL; K.dst[4][idx] = o.fR;
+                K.dst[5][idx] = o.fT; K.dst[6][idx] = o.fB;
+                K.dst[2][idx] = o.water * P.evap;     // sediment_transport.glsl:75
+            }
+            F1(R::RE, SLOT(1, 2), e) = in ? er.rock : HG_OOB_HEIGHT;
+            F1(R::DE, SLOT(1, 8), e) = in ? er.dirt : HG_OOB_HEIGHT;
+            HgF2 s; s.x = in ? er.sr : 0.0f; s.y = in ? er.sd : 0.0f;
+            F2(R::SS, SLOT(1, 4), e) = s;
+        }
+    }
+
+    // ------------------------------------------------------------ B(i-3)
+    {
+        const int yb = i - 3;
+        if (FREE || (yb >= gy0 && yb < gy1)) {
+            HgBack b = hg_backtrace(P, x, yb, W, H, c.u_d2, c.v_d2);
+            const int dx = b.px - x, dy = b.py - yb;
+            const bool fast = dx >= -1 && dx <= 0 && dy >= -1 && dy <= 0;
+            const int cdx = fast ? dx : 0;
+            const bool up = fast && dy == -1;          // footprint rows (yb-1, yb) instead of (yb, yb+1)
+            const int r0 = up ? SLOT(4, 4) : SLOT(3, 4), r1 = up ? SLOT(3, 4) : SLOT(2, 4);
+            const HgF2 t00 = F2(R::SS, r0, e + cdx), t10 = F2(R::SS, r0, e + cdx + 1);
+            const HgF2 t01 = F2(R::SS, r1, e + cdx), t11 = F2(R::SS, r1, e + cdx + 1);
+            float sr = hg_bilerp(t00.x, t10.x, t01.x, t11.x, b.sx, b.sy);
+            float sd = hg_bilerp(t00.y, t10.y, t01.y, t11.y, b.sx, b.sy);
+            if (owned) {
+                const unsigned idx = off - 3u * pitch;
+                if (fast) {
+                    K.dst[7][idx] = sr;
+                    K.dst[8][idx] = sd;
+                } else {
+                    unsigned long long slot = HGF_ATOMIC_INC64(K.far_count);
+                    K.far_list[slot] = (unsigned)(yb - K.row0) * (unsigned)W + (unsigned)x;
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------ C(i-3), D(i-5)
+    {
+        const float rockE_d = c.e01;     // rockE of row i-5 leaves the window now; D needs it
+        c.e00 = c.e10; c.e01 = c.e11; c.e02 = c.e12; c.e10 = c.e20; c.e11 = c.e21; c.e12 = c.e22;
+        c.e20 = F1(R::RE, SLOT(2, 2), e - 1); c.e21 = F1(R::RE, SLOT(2, 2), e); c.e22 = F1(R::RE, SLOT(2, 2), e + 1);
+        const int yc = i - 3;
+        float so0 = 0.0f, T0 = 0.0f, B0 = 0.0f;
+        if (FREE || (yc >= gy0 - 4 && yc < gy1 + 4)) {
+            const bool in = xin && (FREE || (yc >= 0 && yc < H));
+            float out[8], d_h[8];
+            // L R T B LT RT LB RB; window rows: 0 = y-1, 1 = y, 2 = y+1.  The shader's "0 +" is
+            // dropped: it can only turn a -0 difference into +0, and a zero d_h is never marked.
+            d_h[0] = c.e11 - c.e10; d_h[1] = c.e11 - c.e12; d_h[2] = c.e11 - c.e21; d_h[3] = c.e11 - c.e01;
+            d_h[4] = c.e11 - c.e20; d_h[5] = c.e11 - c.e22; d_h[6] = c.e11 - c.e00; d_h[7] = c.e11 - c.e02;
+            if (!in) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) d_h[k] = -1.0f;   // an out-of-map cell has no outflow
+            }
+            so0 = hg_thermal_outflow(P, 0, c.e11, d_h, out);
+            T0 = out[2]; B0 = out[3];
+            HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;    // R, RT, RB
+            HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;    // L, LT, LB
+            F4(R::O0R, SLOT(3, 2), e) = tr;
+            F4(R::O0L, SLOT(3, 2), e) = tl;
+        }
+        // D(i-5): neighbours' outflow of row i-4 (written last iteration)
+        const int yd = i - 5;
+        const HgF4 nl = F4(R::O0R, SLOT(4, 2), e - 1);     // left neighbour's R, RT, RB
+        const HgF4 nr = F4(R::O0L, SLOT(4, 2), e + 1);     // right neighbour's L, LT, LB
+        if (FREE || (yd >= gy0 - 3 && yd < gy1 + 3)) {
+            const bool in = xin && (FREE || (yd >= 0 && yd < H));
+            float delta = hg_thermal_delta(c.so0_d2, c.nR0_d1, c.nL0_d1, c.B0_d1, c.T0_d3, nl.z, nr.z, c.nRT0_d2, c.nLT0_d2);
+            HgF2 w; w.x = in ? rockE_d + delta : HG_OOB_HEIGHT; w.y = F1(R::DE, SLOT(5, 8), e);
+            F2(R::R1D, SLOT(5, 2), e) = w;
+        }
+        c.so0_d2 = c.so0_d1; c.so0_d1 = so0;
+        c.T0_d3 = c.T0_d2; c.T0_d2 = c.T0_d1; c.T0_d1 = T0;
+        c.B0_d1 = B0;
+        c.nR0_d1 = nl.x; c.nL0_d1 = nr.x;
+        c.nRT0_d2 = c.nRT0_d1; c.nRT0_d1 = nl.y; c.nLT0_d2 = c.nLT0_d1; c.nLT0_d1 = nr.y;
+    }
+
+    // ------------------------------------------------------------ E(i-7), F(i-9)
+    {
+        const float rock1_d = c.p01, dirtE_d = c.q01;     // (rock1, dirtE) of row i-9
+        c.p00 = c.p10; c.p01 = c.p11; c.p02 = c.p12; c.p10 = c.p20; c.p11 = c.p21; c.p12 = c.p22;
+        c.q00 = c.q10; c.q01 = c.q11; c.q02 = c.q12; c.q10 = c.q20; c.q11 = c.q21; c.q12 = c.q22;
+        {
+            const HgF2 a = F2(R::R1D, SLOT(6, 2), e - 1), b = F2(R::R1D, SLOT(6, 2), e), d = F2(R::R1D, SLOT(6, 2), e + 1);
+            c.p20 = a.x; c.q20 = a.y; c.p21 = b.x; c.q21 = b.y; c.p22 = d.x; c.q22 = d.y;
+        }
+        const int ye = i - 7;
+        float so1 = 0.0f, T1 = 0.0f, B1 = 0.0f;
+        if (FREE || (ye >= gy0 - 2 && ye < gy1 + 2)) {
+            const bool in = xin && (FREE || (ye >= 0 && ye < H));
+            float out[8], d_h[8];
+            d_h[0] = (c.p11 - c.p10) + (c.q11 - c.q10); d_h[1] = (c.p11 - c.p12) + (c.q11 - c.q12);
+            d_h[2] = (c.p11 - c.p21) + (c.q11 - c.q21); d_h[3] = (c.p11 - c.p01) + (c.q11 - c.q01);
+            d_h[4] = (c.p11 - c.p20) + (c.q11 - c.q20); d_h[5] = (c.p11 - c.p22) + (c.q11 - c.q22);
+            d_h[6] = (c.p11 - c.p00) + (c.q11 - c.q00); d_h[7] = (c.p11 - c.p02) + (c.q11 - c.q02);
+            if (!in) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) d_h[k] = -1.0f;
+            }
+            so1 = hg_thermal_outflow(P, 1, c.q11, d_h, out);
+            T1 = out[2]; B1 = out[3];
+            HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;
+            HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;
+            F4(R::O1R, SLOT(7, 2), e) = tr;
+            F4(R::O1L, SLOT(7, 2), e) = tl;
+        }
+        const int yf = i - 9;
+        const HgF4 nl = F4(R::O1R, SLOT(8, 2), e - 1);
+        const HgF4 nr = F4(R::O1L, SLOT(8, 2), e + 1);
+        if (FREE || (yf >= gy0 - 1 && yf < gy1 + 1)) {
+            const bool in = xin && (FREE || (yf >= 0 && yf < H));
+            float delta = hg_thermal_delta(c.so1_d2, c.nR1_d1, c.nL1_d1, c.B1_d1, c.T1_d3, nl.z, nr.z, c.nRT1_d2, c.nLT1_d2);
+            HgF2 w; w.x = rock1_d; w.y = in ? dirtE_d + delta : HG_OOB_HEIGHT;
+            F2(R::G2, SLOT(9, 4), e) = w;
+        }
+        c.so1_d2 = c.so1_d1; c.so1_d1 = so1;
+        c.T1_d3 = c.T1_d2; c.T1_d2 = c.T1_d1; c.T1_d1 = T1;
+        c.B1_d1 = B1;
+        c.nR1_d1 = nl.x; c.nL1_d1 = nr.x;
+        c.nRT1_d2 = c.nRT1_d1; c.nRT1_d1 = nl.y; c.nLT1_d2 = c.nLT1_d1; c.nLT1_d1 = nr.y;
+    }
+
+    // ------------------------------------------------------------ G(i-11)
+    {
+        // own column of (rock1, dirt2): rows i-12, i-11, i-10 (row i-10 was written last iteration)
+        const HgF2 own = F2(R::G2, SLOT(10, 4), e);
+        c.g_r0 = c.g_r1; c.g_r1 = c.g_r2; c.g_r2 = own.x;
+        c.g_d0 = c.g_d1; c.g_d1 = c.g_d2; c.g_d2 = own.y;
+        const int yg = i - HGF_LAG_G;
+        if (FREE || (yg >= gy0 && yg < gy1)) {
+            const HgF2 l = F2(R::G2, SLOT(11, 4), e - 1), r = F2(R::G2, SLOT(11, 4), e + 1);
+            float rock = c.g_r1, dirt = c.g_d1;
+            float sr_ = rock, sd_ = dirt;
+            hg_smooth_cell(P, sr_, sd_, l.x, l.y, r.x, r.y, c.g_r2, c.g_d2, c.g_r0, c.g_d0);
+            const bool border = (x == 0 || x == W - 1 || (!FREE && (yg == 0 || yg == H - 1)));
+            if (owned) {
+                const unsigned idx = off - (unsigned)HGF_LAG_G * pitch;
+                K.dst[0][idx] = border ? rock : sr_;
+                K.dst[1][idx] = border ? dirt : sd_;
+            }
+        }
+    }
+
+    c.u_d2 = c.u_d1; c.v_d2 = c.v_d1; c.u_d1 = u_new; c.v_d1 = v_new;
+#undef SLOT
+#undef F4
+#undef F2
+#undef F1
+}
+
+// The rows of segment [gy0, gy1) for which FREE iterations are legal: every stage row is
+// inside its active range and strictly inside the map.  Inclusive bounds on i.
+HG_FN void hg_fused_free_range(int gy0, int gy1, int H, int* lo, int* hi) {
+    int l = gy0 + HGF_LAG_G; if (l < 12) l = 12;
+    int h = gy1 + 2; if (h > H - 2) h = H - 2;
+    *lo = l; *hi = h;
+}
+
+// Iteration plan of one CTA: generic iterations [i_begin, free_lo), FREE iterations
+// [free_lo, free_hi], then generic iterations up to i_end inclusive.
+struct HgFusedPlan { int i_begin, i_end, free_lo, free_hi; };
+HG_FN HgFusedPlan hg_fused_plan(int gy0, int gy1, int H) {
+    HgFusedPlan p;
+    p.i_begin = gy0 - HGF_HX;
+    p.i_end = gy1 + HGF_LAG_G - 1;
+    hg_fused_free_range(gy0, gy1, H, &p.free_lo, &p.free_hi);
+    if (p.free_hi < p.free_lo) { p.free_lo = p.i_end + 1; p.free_hi = p.i_end; }
+    return p;
+}
+
+// state before the first iteration: zeroed history, raw row i_begin in flight
+HG_FN void hg_fused_begin(HgCol& c, const HgFusedK& K, bool xin, int i_begin, unsigned off) {
+    hg_col_init(c);
+    const bool ld = xin && i_begin >= 0 && i_begin < K.H;
+#pragma unroll
+    for (int p = 0; p < HGF_NPL; p++) c.pf[p] = ld ? HGF_LDG(K.src[p] + off) : 0.0f;
+}

@@ -78,6 +78,8 @@ struct hg_ctx {
     unsigned long long* d_counters;
     unsigned* far_list;        // cells whose back-trace left the on-chip window this step (lazy)
     int far_parity;
+    int tune_variant;          // CTA shape of the fused kernel; -1 = default (HG_FUSED_VARIANT env at create)
+    int tune_seg;              // rows per CTA of the fused kernel; 0 = automatic (HG_FUSED_SEG env at create)
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
 

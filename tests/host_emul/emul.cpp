@@ -3,10 +3,12 @@
 // TEST INFRASTRUCTURE for `-m "not gpu"`: it checks, on a machine without a GPU, that the
 // device functions reproduce the oracle bit for bit.  It is not a CPU fallback: nothing in
 // the product links or loads it.
+#include <cstdint>
 #include <cstring>
 #include <vector>
 #include "../../hydro_gen_b200/csrc/hg_cell.cuh"
 #include "../../hydro_gen_b200/csrc/hg_noise.cuh"
+#include "../../hydro_gen_b200/csrc/hg_fused_body.cuh"
 
 namespace {
 struct Dom { int W, H; };
@@ -110,4 +112,61 @@ void emul_rain(const hg_rain_data* set, const hg_map_settings_data* map_set, flo
         water[i] += hg_rain_cell(*set, *map_set, time, x, y, rock[i] + dirt[i] + water[i]);
     }
 }
+}
+
+// The fused kernel's body (hg_fused_body.cuh) run thread by thread: CTAs one after the other,
+// inside a CTA all threads execute iteration i before any executes i+1 (the kernel's one
+// barrier per row), with the same generic / FREE iteration plan as k_fused_step.
+// src/dst: 9 planes of W*H floats (no ghost rows).  far_out receives the local cell indices
+// whose sediment the kernel leaves to the far-fetch fix-up; returns their number.
+template <int NT>
+static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    const int HALO = 8;
+    size_t pe = (size_t)(H + 2 * HALO) * W;
+    std::vector<std::vector<float>> ps(9, std::vector<float>(pe, 0.0f)), pd(9, std::vector<float>(pe, 0.0f));
+    for (int p = 0; p < 9; p++) memcpy(ps[p].data() + (size_t)HALO * W, src[p], (size_t)W * H * 4);
+    unsigned long long far_count = 0;
+    HgFusedK K;
+    memset(&K, 0, sizeof(K));
+    for (int p = 0; p < 9; p++) { K.src[p] = ps[p].data(); K.dst[p] = pd[p].data(); }
+    K.W = W; K.H = H; K.row0 = 0; K.rows = H; K.pitch = W; K.seg = seg;
+    K.nstrips = (W + (NT - 12) - 1) / (NT - 12);
+    K.far_list = far_out; K.far_count = &far_count;
+    K.P = hg_make_step_params(*set);
+    int nseg = (H + seg - 1) / seg;
+    std::vector<float> sm(HgRings<NT>::TOTAL + 4);
+    std::vector<HgCol> cols(NT);
+    for (int blk = 0; blk < K.nstrips * nseg; blk++) {
+        std::fill(sm.begin(), sm.end(), 0.0f);
+        float* smp = sm.data();
+        while ((uintptr_t)smp % 16) smp++;
+        int strip = blk % K.nstrips, segi = blk / K.nstrips;
+        int gy0 = segi * seg, gy1 = gy0 + seg < H ? gy0 + seg : H;
+        HgFusedPlan pl = hg_fused_plan(gy0, gy1, H);
+        auto xof = [&](int tid) { return strip * (NT - 12) - 6 + tid; };
+        auto offof = [&](int tid, int i) { return (unsigned)(i + HALO) * (unsigned)W + (unsigned)xof(tid); };
+        for (int tid = 0; tid < NT; tid++) {
+            int x = xof(tid);
+            hg_fused_begin(cols[tid], K, x >= 0 && x < W, pl.i_begin, offof(tid, pl.i_begin));
+        }
+        for (int i = pl.i_begin; i <= pl.i_end; i++) {
+            bool fr = i >= pl.free_lo && i <= pl.free_hi;
+            for (int tid = 0; tid < NT; tid++) {
+                int x = xof(tid);
+                bool xin = x >= 0 && x < W, owned = tid >= 6 && tid < NT - 6 && x < W;
+                unsigned off = offof(tid, i);
+                if (fr) hg_fused_iter<NT, true>(cols[tid], smp, K, tid, x, xin, owned, gy0, gy1, i, off);
+                else hg_fused_iter<NT, false>(cols[tid], smp, K, tid, x, xin, owned, gy0, gy1, i, off);
+            }
+        }
+    }
+    for (int p = 0; p < 9; p++) memcpy(dst[p], pd[p].data() + (size_t)HALO * W, (size_t)W * H * 4);
+    return (long)far_count;
+}
+
+extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt, int seg, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    if (nt == 32) return fused_step_emul<32>(set, W, H, seg, src, dst, far_out);
+    if (nt == 128) return fused_step_emul<128>(set, W, H, seg, src, dst, far_out);
+    if (nt == 256) return fused_step_emul<256>(set, W, H, seg, src, dst, far_out);
+    return -1;
 }
