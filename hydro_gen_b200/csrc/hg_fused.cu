@@ -16,6 +16,7 @@
 //
 // All arithmetic is the shared per-cell code of hg_cell.cuh: results are bit-identical to
 // the PASSES schedule and to the CPU oracle.
+#include <cuda.h>
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
 
@@ -105,12 +106,54 @@ __global__ void __launch_bounds__(128) k_far_fixup(const __grid_constant__ Fused
 }
 
 // ------------------------------------------------------------------ main kernel
+// TMA / mbarrier primitives (PTX ISA 8.x, sm_90+): one elected thread arms an mbarrier with
+// the byte count of a box and issues cp.async.bulk.tensor; every thread waits on the phase.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra HG_DONE_%=;\n"
+        "bra HG_WAIT_%=;\n"
+        "HG_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// The box start column must be a multiple of 4 floats: TMA faults ("illegal instruction") on a
+// start address that is not 16-byte aligned, also with interleave and swizzle off.
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// Shared block: [raw ring: 2 slots x 9 planes x (NT+4) floats, each 128-byte aligned][row rings][2 mbarriers]
+template <int NT> struct FusedSmem {
+    static constexpr size_t RAW_BOX = (size_t)HGF_NPL * HGF_RAW_LD(NT);             // floats delivered per box
+    static constexpr size_t RAW_SLOT = (RAW_BOX + 31) / 32 * 32;                    // slot stride, floats
+    static constexpr size_t RINGS = 2 * RAW_SLOT;                                   // float offset of the row rings
+    static constexpr size_t BARS = (RINGS + HgRings<NT>::TOTAL + 3) / 4 * 4;        // float offset of the mbarriers (16-byte aligned)
+    static constexpr size_t BYTES = (BARS + 4) * sizeof(float);
+};
+
 template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ HgFusedK K) {
-    extern __shared__ __align__(16) float sm[];
+__global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
+    // Dynamic shared memory is the kernel's only shared allocation, so it starts at the CTA's window
+    // base (1 KiB aligned); the TMA destination needs 128 bytes.  (Rounding the pointer up at run
+    // time makes the compiler lose the address space and emit generic LD/ST instead of LDS/STS.)
+    extern __shared__ __align__(128) float smb[];
+    float* const sm = smb + FusedSmem<NT>::RINGS;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
     const int tid = threadIdx.x;
     const int strip = blockIdx.x % K.nstrips, segi = blockIdx.x / K.nstrips;
-    const int x = strip * (NT - 2 * HGF_HX) - HGF_HX + tid;
+    const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
+    const int x = x0 + tid;
     const bool xin = x >= 0 && x < K.W;
     const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
     const int gy0 = K.row0 + segi * K.seg;
@@ -119,49 +162,112 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     const unsigned pitch = (unsigned)K.pitch;
     // element offset of (row i, column x) in a plane, advanced by one row per iteration
     unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
+    const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;      // plane row of iteration i_begin
+    constexpr unsigned BOX_BYTES = (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
+    const int bx0 = x0 - 2;      // box start column: a multiple of 4 (TMA needs a 16-byte aligned start)
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], BOX_BYTES);
+        tma_load_3d(smb, &tmap, &bars[0], bx0, ly0, 0);
+    }
+    __syncthreads();
     HgCol c;
-    hg_fused_begin(c, K, xin, pl.i_begin, off);
+    hg_fused_begin(c);
     int i = pl.i_begin;
-    for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) {
-        hg_fused_iter<NT, false>(c, sm, K, tid, x, xin, owned, gy0, gy1, i, off);
-        __syncthreads();
+    // iteration with relative index rel = i - i_begin: its raw row sits in slot rel & 1, phase (rel >> 1) & 1;
+    // the row of the next iteration is requested first (its slot was last read before the previous barrier).
+    // A deeper ring (3 slots, two rows ahead) was measured and is not faster.
+#define HG_ROW(FREEFLAG)                                                                                             \
+    {                                                                                                                \
+        const int rel = i - pl.i_begin;                                                                              \
+        if (tid == 0 && i < pl.i_end) {                                                                              \
+            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
+            tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
+        }                                                                                                            \
+        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        hg_fused_iter<NT, FREEFLAG>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        __syncthreads();                                                                                             \
     }
+    for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW(false)
 #pragma unroll 1
-    for (; i <= pl.free_hi; i++, off += pitch) {
-        hg_fused_iter<NT, true>(c, sm, K, tid, x, xin, owned, gy0, gy1, i, off);
-        __syncthreads();
-    }
-    for (; i <= pl.i_end; i++, off += pitch) {
-        hg_fused_iter<NT, false>(c, sm, K, tid, x, xin, owned, gy0, gy1, i, off);
-        __syncthreads();
-    }
+    for (; i <= pl.free_hi; i++, off += pitch) HG_ROW(true)
+    for (; i <= pl.i_end; i++, off += pitch) HG_ROW(false)
+#undef HG_ROW
 }
 
 }  // namespace
 
-// NT threads per CTA; seg rows per CTA.  Longer segments amortise the 17-row pipeline fill and
-// the generic (non-FREE) iterations; enough CTAs must remain to fill 148 SMs x resident CTAs.
+// 3-D tensor map over one ping-pong set of the arena: (column, plane row, plane), box (NT+4) x 1 x 9.
+// The box may not exceed 256 columns, so NT <= 252.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap(hg_ctx* c, int set, int nt, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { hg_set_error("cuTensorMapEncodeTiled is not available in this driver"); return HG_ERR_CUDA; }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)c->g.W, (cuuint64_t)c->g.rows_alloc, (cuuint64_t)HG_NPLANES};
+    cuuint64_t strides[2] = {(cuuint64_t)c->g.pitch * sizeof(float), (cuuint64_t)c->g.plane_elems * sizeof(float)};
+    cuuint32_t box[3] = {(cuuint32_t)HGF_RAW_LD(nt), 1u, (cuuint32_t)HG_NPLANES};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, hg_plane(c, set, 0), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hg_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d slab, box %d", (int)r, c->g.W, c->g.rows_alloc, nt); return HG_ERR_CUDA; }
+    return HG_OK;
+}
+
+// NT threads per CTA; seg rows per CTA.
 template <int NT, int MINB>
-static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg) {
+static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     HgFusedK K = K0;
     K.nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
     K.seg = seg;
     int nseg = (c->g.rows + seg - 1) / seg;
-    constexpr size_t smem = (size_t)HgRings<NT>::TOTAL * sizeof(float);
+    constexpr size_t smem = FusedSmem<NT>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         HG_CUDA(cudaFuncSetAttribute(k_fused_step<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    alignas(64) CUtensorMap tmap;
+    int rc = make_tmap(c, src_set, NT, &tmap);
+    if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
-    k_fused_step<NT, MINB><<<K.nstrips * nseg, NT, smem, c->stream>>>(K);
+    k_fused_step<NT, MINB><<<K.nstrips * nseg, NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
 }
 
+// The TMA box spans all nine planes, so the read planes of H, F and S must sit in the same
+// ping-pong set.  They always do on the FUSED schedule (all three flip together, rain is in
+// place); after PASSES dispatches they may not, and the odd ones are copied across once.
+static int align_sets(hg_ctx* c) {
+    const size_t pb = c->g.plane_elems * sizeof(float);
+    if (c->ri[1] != c->ri[0]) {
+        HG_CUDA(cudaMemcpyAsync(hg_plane(c, c->ri[0], PL_FL), hg_plane(c, c->ri[1], PL_FL), 4 * pb, cudaMemcpyDeviceToDevice, c->stream));
+        c->ri[1] = c->ri[0];
+    }
+    if (c->ri[3] != c->ri[0]) {
+        HG_CUDA(cudaMemcpyAsync(hg_plane(c, c->ri[0], PL_SR), hg_plane(c, c->ri[3], PL_SR), 2 * pb, cudaMemcpyDeviceToDevice, c->stream));
+        c->ri[3] = c->ri[0];
+    }
+    return HG_OK;
+}
+
 int hg_launch_fused_step(hg_ctx* c) {
     if (c->g.plane_elems >= (size_t)1 << 32) { hg_set_error("slab too large for 32-bit plane offsets (%zu elements)", c->g.plane_elems); return HG_ERR_INVALID; }
+    int rca = align_sets(c);
+    if (rca) return rca;
     FusedArgs A;
     memset(&A, 0, sizeof(A));
     HgFusedK K;
@@ -187,22 +293,37 @@ int hg_launch_fused_step(hg_ctx* c) {
     A.far_total = c->d_counters;
     c->far_parity ^= 1;
     A.P = K.P = c->sp;
-    // CTA shape (threads, resident CTAs per SM) and rows per CTA; HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
-    static const int nt_of[] = {128, 128, 192, 256, 256};
+    // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
+    static const int nt_of[] = {128, 128, 192, 224, 224};
     static const int res_of[] = {4, 3, 2, 2, 1};
-    int v = c->tune_variant >= 0 && c->tune_variant < 5 ? c->tune_variant : 1;
+    int v = c->tune_variant >= 0 && c->tune_variant < 5 ? c->tune_variant : 0;
     const int NT = nt_of[v];
     int nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
-    int seg = c->tune_seg > 0 ? c->tune_seg : 512;
-    if (c->tune_seg <= 0)   // as long as possible while the grid still fills the resident slots about twice
-        while (seg > 32 && (long long)nstrips * ((c->g.rows + seg - 1) / seg) < 148 * res_of[v] * 2) seg /= 2;
+    // Rows per CTA.  A CTA runs seg + 17 row iterations (pipeline fill), about 8 of them of the
+    // slower non-FREE kind.  An SM's time for a wave of w resident warps was measured as roughly
+    // proportional to 10 + 0.375 w per row iteration (8 warps reach 61 % of the throughput of 16).
+    // Pick the segment count that minimises the sum over the waves of this grid.
+    int seg = c->tune_seg;
+    if (seg <= 0) {
+        const int res = res_of[v], wpc = NT / 32;
+        double best = 1e30;
+        for (int nseg = 1; nseg <= c->g.rows / 16 + 1 && nseg <= 4096; nseg++) {
+            int sg = (c->g.rows + nseg - 1) / nseg;
+            long long ctas = (long long)nstrips * ((c->g.rows + sg - 1) / sg);
+            long long per_sm = (ctas + 147) / 148;                 // CTAs the busiest SM runs
+            long long full = per_sm / res, last = per_sm % res;    // full waves + a partial one
+            double iters = sg + HGF_HX + HGF_LAG_G + 8;
+            double cost = iters * (full * (10.0 + 0.375 * res * wpc) + (last ? 10.0 + 0.375 * last * wpc : 0.0));
+            if (cost < best) { best = cost; seg = sg; }
+        }
+    }
     int rc;
     switch (v) {
-    case 0: rc = launch_main<128, 4>(c, K, seg); break;
-    case 1: rc = launch_main<128, 3>(c, K, seg); break;
-    case 2: rc = launch_main<192, 2>(c, K, seg); break;
-    case 3: rc = launch_main<256, 2>(c, K, seg); break;
-    default: rc = launch_main<256, 1>(c, K, seg); break;
+    case 0: rc = launch_main<128, 4>(c, K, seg, c->ri[0]); break;
+    case 1: rc = launch_main<128, 3>(c, K, seg, c->ri[0]); break;
+    case 2: rc = launch_main<192, 2>(c, K, seg, c->ri[0]); break;
+    case 3: rc = launch_main<224, 2>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);

@@ -6,7 +6,7 @@
 // rows; thread t holds column x0-6+t and marches in +y.  At iteration i every stage works
 // on its own lagged row:
 //
-//   L(i)    raw row i arrives (prefetched one iteration earlier); H.a = (r+g)+b
+//   L(i)    raw row i (TMA-staged in shared memory one iteration earlier); H.a = (r+g)+b
 //   A(i-1)  hydro_flux + hydro_erosion (+ evaporation)  -> F', water' to HBM; rockE, dirtE, S', u, v
 //   B(i-3)  sediment back-trace + bilinear gather of S' -> sediment' to HBM
 //   C(i-3)  thermal outflow, layer 0 (rock)             -> 8 outflows
@@ -51,6 +51,7 @@
 constexpr int HGF_HX = 6;        // halo columns per side
 constexpr int HGF_LAG_G = 11;    // rows between L and G
 constexpr int HGF_NPL = 9;       // rock dirt water fL fR fT fB sr sd (HgPlane order)
+#define HGF_RAW_LD(NT) ((NT) + 4)  // columns per plane row in the TMA-staged raw block
 
 struct HgF4 { float x, y, z, w; };
 struct HgF2 { float x, y; };
@@ -102,7 +103,6 @@ struct HgCol {
     float so1_d1, so1_d2, T1_d1, T1_d2, T1_d3, B1_d1;
     float nR1_d1, nL1_d1, nRT1_d1, nRT1_d2, nLT1_d1, nLT1_d2;
     float g_r0, g_r1, g_r2, g_d0, g_d1, g_d2;    // own column of (rock1, dirt2) rows i-12..i-10
-    float pf[HGF_NPL];                           // raw row i+1 in flight
 };
 
 HG_FN void hg_col_init(HgCol& c) {
@@ -116,7 +116,7 @@ HG_FN void hg_col_init(HgCol& c) {
 // row segment; off: element offset of (row i, column x) inside a plane.
 // FREE: see the header.
 template <int NT, bool FREE>
-HG_FN void hg_fused_iter(HgCol& c, float* sm, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
+HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
                          const int gy0, const int gy1, const int i, const unsigned off) {
     typedef HgRings<NT> R;
     const HgStepParams& P = K.P;
@@ -134,22 +134,21 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const HgFusedK& K, const int tid, 
     // ------------------------------------------------------------ L(i)
     c.rk0 = c.rk1; c.rk1 = c.rk2; c.dt0 = c.dt1; c.dt1 = c.dt2; c.at0 = c.at1; c.at1 = c.at2; c.w1 = c.w2;
     c.f0T = c.f1T; c.f1L = c.f2L; c.f1R = c.f2R; c.f1T = c.f2T; c.f1B = c.f2B; c.s1r = c.s2r; c.s1d = c.s2d;
-    c.rk2 = c.pf[0]; c.dt2 = c.pf[1]; c.w2 = c.pf[2];
-    c.f2L = c.pf[3]; c.f2R = c.pf[4]; c.f2T = c.pf[5]; c.f2B = c.pf[6];
-    c.s2r = c.pf[7]; c.s2d = c.pf[8];
+    // raw row i: nine planes x (NT+4) columns staged in shared memory by one TMA box load; the box
+    // starts 2 columns left of thread 0 because TMA needs a 16-byte aligned start.  Out-of-map
+    // columns and rows arrive as zeros (TMA bounds fill / never-written ghost rows).
+    {
+        const float* rw = raw + tid + 2;
+        constexpr int LD = HGF_RAW_LD(NT);
+        c.rk2 = rw[0 * LD]; c.dt2 = rw[1 * LD]; c.w2 = rw[2 * LD];
+        c.f2L = rw[3 * LD]; c.f2R = rw[4 * LD]; c.f2T = rw[5 * LD]; c.f2B = rw[6 * LD];
+        c.s2r = rw[7 * LD]; c.s2d = rw[8 * LD];
+    }
     c.at2 = (xin && (FREE || (i >= 0 && i < H))) ? c.rk2 + c.dt2 + c.w2 : HG_OOB_HEIGHT;
     {
         HgF4 q; q.x = c.at2; q.y = c.rk2; q.z = c.dt2; q.w = c.f2R;
         F4(R::XQ, SLOT(0, 2), e) = q;
         F1(R::XL, SLOT(0, 2), e) = c.f2L;
-    }
-    // prefetch raw row i+1 (consumed next iteration)
-    {
-        const int gy = i + 1;
-        const bool ld = xin && (FREE || (gy >= 0 && gy < H && gy < gy1 + HGF_HX));
-        const unsigned noff = off + pitch;
-#pragma unroll
-        for (int p = 0; p < HGF_NPL; p++) c.pf[p] = ld ? HGF_LDG(K.src[p] + noff) : 0.0f;
     }
 
     // ------------------------------------------------------------ A(i-1)
@@ -342,10 +341,5 @@ HG_FN HgFusedPlan hg_fused_plan(int gy0, int gy1, int H) {
     return p;
 }
 
-// state before the first iteration: zeroed history, raw row i_begin in flight
-HG_FN void hg_fused_begin(HgCol& c, const HgFusedK& K, bool xin, int i_begin, unsigned off) {
-    hg_col_init(c);
-    const bool ld = xin && i_begin >= 0 && i_begin < K.H;
-#pragma unroll
-    for (int p = 0; p < HGF_NPL; p++) c.pf[p] = ld ? HGF_LDG(K.src[p] + off) : 0.0f;
-}
+// state before the first iteration: zeroed history
+HG_FN void hg_fused_begin(HgCol& c) { hg_col_init(c); }

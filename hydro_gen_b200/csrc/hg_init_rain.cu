@@ -68,10 +68,15 @@ int hg_launch_heightmap(hg_ctx* c) {
 int hg_launch_rain(hg_ctx* c, float time) {
     SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
     dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
+    // The reference writes the other heightmap texture and swaps (erosion.cpp:76-89).  Rain is
+    // pointwise, so on the FUSED schedule it runs in place: H, F and S then stay in the same
+    // ping-pong set, which the fused kernel's nine-plane TMA box needs.
+    const bool in_place = c->schedule == HG_SCHEDULE_FUSED && c->erosion_type == HG_GRID;
+    const int w = in_place ? 1 : 0;
     RainArgs A{hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1), hg_total_live(c) ? hg_total(c, 1) : nullptr,
-               hg_cur(c, PL_ROCK, 0), hg_cur(c, PL_DIRT, 0), hg_cur(c, PL_WATER, 0), c->aux ? hg_total(c, 0) : nullptr};
+               hg_cur(c, PL_ROCK, w), hg_cur(c, PL_DIRT, w), hg_cur(c, PL_WATER, w), c->aux ? hg_total(c, w) : nullptr};
     k_rain<<<g, b, 0, c->stream>>>(d, c->rain, c->map, time, A);
     HG_LAUNCH_CHECK(c);
-    c->ri[0] ^= 1;
+    if (!in_place) c->ri[0] ^= 1;
     return HG_OK;
 }

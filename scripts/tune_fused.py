@@ -38,7 +38,7 @@ def timeit(n, variant, seg, steps=30):
 
 if __name__ == "__main__":
     sizes = [int(a) for a in sys.argv[1:]] or [4096]
-    names = ["128x4", "128x3", "192x2", "256x2", "256x1"]
+    names = ["128x4", "128x3", "192x2", "224x2", "224x1"]
     for v in range(5):
         for seg in (128, 256, 512):
             ok = check(v, seg)

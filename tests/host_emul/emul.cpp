@@ -145,18 +145,21 @@ static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, c
         HgFusedPlan pl = hg_fused_plan(gy0, gy1, H);
         auto xof = [&](int tid) { return strip * (NT - 12) - 6 + tid; };
         auto offof = [&](int tid, int i) { return (unsigned)(i + HALO) * (unsigned)W + (unsigned)xof(tid); };
-        for (int tid = 0; tid < NT; tid++) {
-            int x = xof(tid);
-            hg_fused_begin(cols[tid], K, x >= 0 && x < W, pl.i_begin, offof(tid, pl.i_begin));
-        }
+        for (int tid = 0; tid < NT; tid++) hg_fused_begin(cols[tid]);
+        std::vector<float> raw(9 * HGF_RAW_LD(NT));
         for (int i = pl.i_begin; i <= pl.i_end; i++) {
             bool fr = i >= pl.free_lo && i <= pl.free_hi;
+            // what the kernel's TMA box load delivers: plane rows with zero fill outside the allocation
+            for (int p = 0; p < 9; p++) for (int t = 0; t < HGF_RAW_LD(NT); t++) {
+                int x = xof(0) - 2 + t, lr = i + HALO;
+                raw[p * HGF_RAW_LD(NT) + t] = (x >= 0 && x < W && lr >= 0 && lr < H + 2 * HALO) ? ps[p][(size_t)lr * W + x] : 0.0f;
+            }
             for (int tid = 0; tid < NT; tid++) {
                 int x = xof(tid);
                 bool xin = x >= 0 && x < W, owned = tid >= 6 && tid < NT - 6 && x < W;
                 unsigned off = offof(tid, i);
-                if (fr) hg_fused_iter<NT, true>(cols[tid], smp, K, tid, x, xin, owned, gy0, gy1, i, off);
-                else hg_fused_iter<NT, false>(cols[tid], smp, K, tid, x, xin, owned, gy0, gy1, i, off);
+                if (fr) hg_fused_iter<NT, true>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                else hg_fused_iter<NT, false>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
             }
         }
     }
@@ -167,6 +170,6 @@ static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, c
 extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt, int seg, const float* const src[9], float* const dst[9], unsigned* far_out) {
     if (nt == 32) return fused_step_emul<32>(set, W, H, seg, src, dst, far_out);
     if (nt == 128) return fused_step_emul<128>(set, W, H, seg, src, dst, far_out);
-    if (nt == 256) return fused_step_emul<256>(set, W, H, seg, src, dst, far_out);
+    if (nt == 224) return fused_step_emul<224>(set, W, H, seg, src, dst, far_out);
     return -1;
 }

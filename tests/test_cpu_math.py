@@ -153,7 +153,7 @@ def fused_emul_step(E, w, nt, seg):
     return dst, far[:n]
 
 
-@pytest.mark.parametrize("nt,seg,shape", [(32, 16, (72, 64)), (32, 64, (40, 136)), (128, 32, (192, 96)), (128, 128, (128, 160)), (256, 64, (264, 80))])
+@pytest.mark.parametrize("nt,seg,shape", [(32, 16, (72, 64)), (32, 64, (40, 136)), (128, 32, (192, 96)), (128, 128, (128, 160)), (224, 64, (264, 80))])
 def test_fused_kernel_body_emulated_matches_oracle(emul, nt, seg, shape):
     """hg_fused_body.cuh — the code k_fused_step runs — executed thread by thread on the CPU with
     the kernel's own iteration plan (generic fill/drain + 6x unrolled FREE blocks), against the
