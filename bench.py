@@ -170,9 +170,8 @@ def main():
     m = ctx.get_map(); m.seed = SEED; ctx.set_map(m)
     r = ctx.get_rain(); r.period = 4; ctx.set_rain(r)
     if n > 1:
-        exports = [None] * n
-        dist.all_gather_object(exports, bytes(ctx.export_handle()))
-        ctx.connect([_lib.SlabExport.from_buffer_copy(b) for b in exports], rank)
+        from hydro_gen_b200 import slabs
+        slabs.connect_ring(ctx, dist, n, rank)
     ctx.gen_heightmap()
     if n > 1:
         dist.barrier()

@@ -9,7 +9,7 @@ from ._lib import (FIELD_FLUX, FIELD_HEIGHTMAP, FIELD_SEDIMENT, FIELD_THERMAL_C,
                    HG_GRID, HG_PARTICLES, SCHEDULE_FUSED, SCHEDULE_PASSES, ErosionData, HydrogenError,
                    MapSettingsData, RainData)
 from .context import PARTICLE_DTYPE, Context, PinnedBuffer
-from . import state, erosion, config
+from . import state, erosion, config, slabs
 
-__all__ = ["state", "erosion", "config", "Context", "PinnedBuffer", "ErosionData", "RainData", "MapSettingsData",
+__all__ = ["state", "erosion", "config", "slabs", "Context", "PinnedBuffer", "ErosionData", "RainData", "MapSettingsData",
            "HydrogenError", "PARTICLE_DTYPE"]
