@@ -49,7 +49,7 @@ def read_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -140,10 +140,10 @@ def workload_config(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -228,27 +228,23 @@ def main():
                 "algorithmic_bytes_per_cell_step": ALG_BYTES_PER_CELL, "cells_per_launch": W * rows,
                 "note": "the kernel is fp32-issue bound, not HBM bound (DESIGN.md §Roofline)"}
 
-    # end to end through the C ABI with host buffers: upload H,F,S (pinned, RGBA32F) -> step -> download H,F,S
+    # end to end through the C ABI with HOST buffers: every step uploads H, F, S from pinned RGBA32F
+    # images (the reference's texture format), steps, and downloads H, F, S into a second set.
+    # hg_step_host_async pipelines consecutive steps over copy streams (PCIe is full duplex).
     fields = (_lib.FIELD_HEIGHTMAP, _lib.FIELD_FLUX, _lib.FIELD_SEDIMENT)
     pins = [PinnedBuffer((rows, W, 4)) for _ in fields]
+    pouts = [PinnedBuffer((rows, W, 4)) for _ in fields]
     for f, p in zip(fields, pins):
         ctx.download(f, p.array)
+    ins, outs = [p.array for p in pins], [p.array for p in pouts]
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     for _ in range(2):      # warm the staging path
-        for f, p in zip(fields, pins):
-            ctx.upload(f, p.array, asynchronous=True)
-        ctx.dispatch_grid()
-        for f, p in zip(fields, pins):
-            ctx.download(f, p.array, asynchronous=True)
+        ctx.step_host_async(ins, outs)
     barrier()
     ctx.timer_start()
     for _ in range(e2e_steps):
-        for f, p in zip(fields, pins):
-            ctx.upload(f, p.array, asynchronous=True)
-        ctx.dispatch_grid()
-        for f, p in zip(fields, pins):
-            ctx.download(f, p.array, asynchronous=True)
-    e_ms = ctx.timer_stop()
+        ctx.step_host_async(ins, outs)
+    e_ms = ctx.timer_stop()     # waits for the last download
     barrier()
     if n > 1:
         import torch
@@ -259,7 +255,8 @@ def main():
     bytes_dir = len(fields) * rows * W * 16
     e2e = {"value": e2e_val, "unit": "Gcell-steps/s", "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
            "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
-           "what": "per step: hg_upload_async(H,F,S) from pinned RGBA32F host buffers, hg_dispatch_grid, hg_download_async(H,F,S)"}
+           "what": "per step: hg_step_host_async = upload H,F,S from pinned RGBA32F host images, Erosion::dispatch_grid, "
+                   "download H,F,S to a second pinned set; consecutive steps pipelined over 3 streams"}
     halo_errors = ctx.slab_errors()
 
     if rank == 0:
@@ -272,7 +269,7 @@ def main():
             v, threads, sample = cpu_baseline(W, 256, 100)
             line["cpu_baseline"] = {"value": v, "unit": "Gcell-steps/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
-    for p in pins:
+    for p in pins + pouts:
         p.free()
     ctx.close()
     if n > 1:

@@ -86,6 +86,7 @@ SYMBOLS = {
     "hg_download_async": (_i, [_vp, _i, _vp]),
     "hg_upload_particles": (_i, [_vp, _vp, _u]),
     "hg_download_particles": (_i, [_vp, _vp, _u]),
+    "hg_step_host_async": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hg_host_alloc": (_vp, [C.c_size_t]),
     "hg_host_free": (None, [_vp]),
     "hg_mass": (_i, [_vp, C.POINTER(C.c_double)]),

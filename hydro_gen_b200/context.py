@@ -138,6 +138,14 @@ class Context:
         check(fn(self.h, int(field), out.ctypes.data))
         return out
 
+    def step_host_async(self, ins, outs):
+        """hg_step_host_async: one dispatch_grid from host images (H, F, S) to host images, pipelined
+        over copy streams.  `ins`/`outs`: three float32 (rows, W, 4) arrays each (pinned for overlap);
+        none of them may be touched before sync()."""
+        for a in list(ins) + list(outs):
+            assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.size == self.rows * self.W * 4
+        check(self.L.hg_step_host_async(self.h, *[a.ctypes.data for a in ins], *[a.ctypes.data for a in outs]))
+
     def upload_particles(self, arr):
         a = np.ascontiguousarray(arr, dtype=PARTICLE_DTYPE)
         check(self.L.hg_upload_particles(self.h, a.ctypes.data, a.shape[0]))

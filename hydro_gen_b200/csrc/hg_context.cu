@@ -29,6 +29,14 @@ static void free_ctx(hg_ctx* c) {
     if (c->particles) cudaFree(c->particles);
     if (c->lockmap) cudaFree(c->lockmap);
     if (c->staging) cudaFree(c->staging);
+    if (c->stage_up) cudaFree(c->stage_up);
+    if (c->stage_down) cudaFree(c->stage_down);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->ev_comp) cudaEventDestroy(c->ev_comp);
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    if (c->ev_down) cudaEventDestroy(c->ev_down);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->far_list) cudaFree(c->far_list);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -363,9 +371,87 @@ extern "C" int hg_mass(hg_ctx* c, double out5[5]) {
     return HG_OK;
 }
 
+// ---- pipelined host step --------------------------------------------------------------
+// One Erosion::dispatch_grid whose inputs come from, and whose results go to, HOST images in the
+// reference's texture format (RGBA32F H, F, S).  Three streams: uploads + unpack, the step, pack +
+// downloads; consecutive calls overlap (PCIe is full duplex): the upload of call k+1 runs while
+// call k computes and downloads.  Host buffers should be pinned (hg_host_alloc); outputs are
+// valid after hg_sync.  Ordering: unpack(k+1) overwrites the planes pack(k) reads, so it waits
+// for ev_packed; staging buffers are reused in stream order.
+static int ensure_host_pipe(hg_ctx* c) {
+    if (c->stage_up) return HG_OK;
+    const size_t bytes = (size_t)3 * c->g.rows * c->g.W * 4 * sizeof(float);
+    HG_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    HG_CUDA(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+    HG_CUDA(cudaMalloc(&c->stage_up, bytes));
+    HG_CUDA(cudaMalloc(&c->stage_down, bytes));
+    HG_CUDA(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    HG_CUDA(cudaEventCreateWithFlags(&c->ev_comp, cudaEventDisableTiming));
+    HG_CUDA(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    HG_CUDA(cudaEventCreate(&c->ev_down));
+    return HG_OK;
+}
+
+extern "C" int hg_step_host_async(hg_ctx* c, const float* in_h, const float* in_f, const float* in_s,
+                                  float* out_h, float* out_f, float* out_s) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_GRID || c->schedule != HG_SCHEDULE_FUSED) { hg_set_error("hg_step_host_async needs a grid context on the FUSED schedule"); return HG_ERR_STATE; }
+    if (!in_h || !in_f || !in_s || !out_h || !out_f || !out_s) { hg_set_error("null host image"); return HG_ERR_INVALID; }
+    int rc = ensure_host_pipe(c);
+    if (rc) return rc;
+    const int fields[3] = {HG_FIELD_HEIGHTMAP, HG_FIELD_FLUX, HG_FIELD_SEDIMENT};
+    const float* in[3] = {in_h, in_f, in_s};
+    float* out[3] = {out_h, out_f, out_s};
+    const size_t n = (size_t)c->g.rows * c->g.W;            // texels per field
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    // uploads: everything already enqueued on the main stream (a previous plain dispatch, an
+    // upload ...) must be done with the planes before they are overwritten
+    HG_CUDA(cudaEventRecord(c->ev_comp, c->stream));
+    HG_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_comp, 0));
+    for (int k = 0; k < 3; k++)
+        HG_CUDA(cudaMemcpyAsync(c->stage_up + (size_t)k * n * 4, in[k], n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->up_stream));
+    if (c->host_pipe_busy) HG_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_packed, 0));
+    for (int k = 0; k < 3; k++) {
+        Chan4 ch; int synth;
+        rc = field_channels(c, fields[k], &ch, &synth, true);
+        if (rc) return rc;
+        k_unpack<<<blocks, 256, 0, c->up_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<const float4*>(c->stage_up + (size_t)k * n * 4));
+        HG_LAUNCH_CHECK(c);
+    }
+    HG_CUDA(cudaEventRecord(c->ev_up, c->up_stream));
+    // the step
+    HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    rc = hg_launch_fused_step(c);
+    if (rc) return rc;
+    rc = hg_slab_exchange(c);
+    if (rc) return rc;
+    HG_CUDA(cudaEventRecord(c->ev_comp, c->stream));
+    // pack + downloads
+    HG_CUDA(cudaStreamWaitEvent(c->down_stream, c->ev_comp, 0));
+    for (int k = 0; k < 3; k++) {
+        Chan4 ch; int synth;
+        rc = field_channels(c, fields[k], &ch, &synth, false);
+        if (rc) return rc;
+        k_pack<<<blocks, 256, 0, c->down_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<float4*>(c->stage_down + (size_t)k * n * 4), synth);
+        HG_LAUNCH_CHECK(c);
+    }
+    HG_CUDA(cudaEventRecord(c->ev_packed, c->down_stream));
+    for (int k = 0; k < 3; k++)
+        HG_CUDA(cudaMemcpyAsync(out[k], c->stage_down + (size_t)k * n * 4, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->down_stream));
+    HG_CUDA(cudaEventRecord(c->ev_down, c->down_stream));
+    c->host_pipe_busy = true;
+    return HG_OK;
+}
+
 // ------------------------------------------------------- streams, sync, timing
 
-extern "C" int hg_sync(hg_ctx* c) { HG_CHECK_CTX(c); HG_CUDA(cudaStreamSynchronize(c->stream)); return HG_OK; }
+extern "C" int hg_sync(hg_ctx* c) {
+    HG_CHECK_CTX(c);
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->up_stream) HG_CUDA(cudaStreamSynchronize(c->up_stream));
+    if (c->down_stream) HG_CUDA(cudaStreamSynchronize(c->down_stream));
+    return HG_OK;
+}
 extern "C" int hg_set_stream(hg_ctx* c, void* s) {
     HG_CHECK_CTX(c);
     HG_CUDA(cudaStreamSynchronize(c->stream));
@@ -377,6 +463,7 @@ extern "C" void* hg_get_stream(hg_ctx* c) { return c ? static_cast<void*>(c->str
 extern "C" int hg_timer_start(hg_ctx* c) { HG_CHECK_CTX(c); HG_CUDA(cudaEventRecord(c->ev0, c->stream)); return HG_OK; }
 extern "C" int hg_timer_stop(hg_ctx* c, float* ms) {
     HG_CHECK_CTX(c);
+    if (c->host_pipe_busy) HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_down, 0));   // include the last download
     HG_CUDA(cudaEventRecord(c->ev1, c->stream));
     HG_CUDA(cudaEventSynchronize(c->ev1));
     if (ms) HG_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));

@@ -82,6 +82,12 @@ struct hg_ctx {
     int tune_seg;              // rows per CTA of the fused kernel; 0 = automatic (HG_FUSED_SEG env at create)
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
+    // pipelined host step (hg_step_host_async): copy streams, full-size staging, ordering events
+    cudaStream_t up_stream, down_stream;
+    float* stage_up;           // 3 fields x rows x W x 4 floats (H, F, S as RGBA32F)
+    float* stage_down;
+    cudaEvent_t ev_up, ev_comp, ev_packed, ev_down;
+    bool host_pipe_busy;       // ev_packed / ev_down have been recorded at least once
 
     // multi-GPU slabs (hg_slab.cu): every rank's arena, ordered by row0
     HgSlabTable slabs;

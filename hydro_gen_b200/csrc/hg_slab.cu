@@ -20,30 +20,47 @@
 
 namespace {
 
+struct PushSide {
+    float* dst[HG_NPLANES];         // neighbour's planes (same set), local row 0; nullptr = no neighbour on this side
+    size_t src_off, dst_off;        // element offsets of the first row to copy
+};
+struct FlagArgs { unsigned* flag[HG_MAX_SLABS]; int n; };
 struct PushArgs {
     const float* src[HG_NPLANES];   // my planes (current read set), local row 0
-    float* dst[HG_NPLANES];         // neighbour's planes, same set
-    size_t src_off, dst_off;        // element offsets of the first row to copy
-    size_t n;                       // elements per plane (HG_HALO_ROWS * pitch)
+    PushSide side[2];
+    size_t n;                       // elements per plane and side (HG_HALO_ROWS * pitch)
+    FlagArgs sig;                   // my flag word on every other rank
+    unsigned gen;
+    unsigned* done;                 // block counter (self-resetting)
 };
 
-// float4 copy of HG_HALO_ROWS rows x 9 planes into the neighbour's ghost rows
-__global__ void __launch_bounds__(256) k_halo_push(PushArgs A) {
-    int plane = blockIdx.y;
-    const float4* s = reinterpret_cast<const float4*>(A.src[plane] + A.src_off);
-    float4* d = reinterpret_cast<float4*>(A.dst[plane] + A.dst_off);
-    size_t n4 = A.n / 4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+// One kernel per step: float4 copy of HG_HALO_ROWS rows x 9 planes into each neighbour's ghost
+// rows (blockIdx.y = plane, blockIdx.z = side); the last block to finish publishes the step
+// number `gen` in this rank's flag word on every rank.
+__global__ void __launch_bounds__(256) k_halo_push_signal(PushArgs A) {
+    const int plane = blockIdx.y, sd = blockIdx.z;
+    if (A.side[sd].dst[plane]) {
+        const float4* s = reinterpret_cast<const float4*>(A.src[plane] + A.side[sd].src_off);
+        float4* d = reinterpret_cast<float4*>(A.side[sd].dst[plane] + A.side[sd].dst_off);
+        size_t n4 = A.n / 4;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned last;
+    if (threadIdx.x == 0) {
+        unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        last = (atomicAdd(A.done, 1u) == total - 1);
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *A.done = 0u;
+        __threadfence_system();
+        if ((int)threadIdx.x < A.sig.n && A.sig.flag[threadIdx.x]) *reinterpret_cast<volatile unsigned*>(A.sig.flag[threadIdx.x]) = A.gen;
+        __threadfence_system();
+    }
 }
 
-struct FlagArgs { unsigned* flag[HG_MAX_SLABS]; int n; };
-
-// after the pushes of this step, in stream order: write `gen` into my word on every rank
-__global__ void k_halo_signal(FlagArgs F, unsigned gen) {
-    __threadfence_system();
-    if ((int)threadIdx.x < F.n && F.flag[threadIdx.x]) *reinterpret_cast<volatile unsigned*>(F.flag[threadIdx.x]) = gen;
-    __threadfence_system();
-}
 // bounded spin until every rank's word in MY flag page reached `gen`; on timeout it records
 // an error instead of hanging the GPU
 __global__ void k_halo_wait(FlagArgs F, unsigned gen, unsigned long long* err) {
@@ -174,37 +191,36 @@ int hg_slab_exchange(hg_ctx* c) {
     c->step_flag++;
     const unsigned gen = c->step_flag;
     const size_t rowsz = (size_t)c->g.pitch;
+    PushArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int p = 0; p < HG_NPLANES; p++) A.src[p] = hg_plane(c, c->ri[hg_field_of_plane(p)], p);
+    A.n = (size_t)HG_HALO_ROWS * rowsz;
     for (int s = 0; s < 2; s++) {
         int nb = T.me + (s == 0 ? -1 : 1);
         if (nb < 0 || nb >= T.n) continue;
-        PushArgs A;
         size_t nb_elems = plane_elems_of(c, nb);
-        for (int p = 0; p < HG_NPLANES; p++) {
-            int set = c->ri[hg_field_of_plane(p)];
-            A.src[p] = hg_plane(c, set, p);
-            A.dst[p] = T.arena[nb] + ((size_t)set * HG_NPLANES + p) * nb_elems;
-        }
-        A.n = (size_t)HG_HALO_ROWS * rowsz;
+        for (int p = 0; p < HG_NPLANES; p++)
+            A.side[s].dst[p] = T.arena[nb] + ((size_t)c->ri[hg_field_of_plane(p)] * HG_NPLANES + p) * nb_elems;
         if (s == 0) {   // my first owned rows -> lower neighbour's upper ghost rows
-            A.src_off = (size_t)HG_HALO_ROWS * rowsz;
-            A.dst_off = (size_t)(HG_HALO_ROWS + T.rows[nb]) * rowsz;
+            A.side[s].src_off = (size_t)HG_HALO_ROWS * rowsz;
+            A.side[s].dst_off = (size_t)(HG_HALO_ROWS + T.rows[nb]) * rowsz;
         } else {        // my last owned rows -> upper neighbour's lower ghost rows
-            A.src_off = (size_t)c->g.rows * rowsz;
-            A.dst_off = 0;
+            A.side[s].src_off = (size_t)c->g.rows * rowsz;
+            A.side[s].dst_off = 0;
         }
-        size_t blocks = (A.n / 4 + 255) / 256;
-        dim3 grid((unsigned)(blocks < 64 ? blocks : 64), HG_NPLANES);
-        k_halo_push<<<grid, 256, 0, c->stream>>>(A);
-        HG_LAUNCH_CHECK(c);
     }
-    FlagArgs S{}, Wt{};
-    S.n = Wt.n = T.n;
+    FlagArgs Wt{};
+    A.sig.n = Wt.n = T.n;
     for (int k = 0; k < T.n; k++) {
         if (k == T.me) continue;
-        S.flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);     // my word on rank k
-        Wt.flag[k] = flag_ptr(c->arena, c->g.plane_elems, k);             // rank k's word on me
+        A.sig.flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);   // my word on rank k
+        Wt.flag[k] = flag_ptr(c->arena, c->g.plane_elems, k);               // rank k's word on me
     }
-    k_halo_signal<<<1, 32, 0, c->stream>>>(S, gen);
+    A.gen = gen;
+    A.done = reinterpret_cast<unsigned*>(c->d_counters + 10);
+    size_t blocks = (A.n / 4 + 255) / 256;
+    dim3 grid((unsigned)(blocks < 16 ? blocks : 16), HG_NPLANES, 2);
+    k_halo_push_signal<<<grid, 256, 0, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);
     k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, gen, c->d_counters + 1);
     HG_LAUNCH_CHECK(c);

@@ -117,6 +117,14 @@ int hg_download_particles(hg_ctx* ctx, hg_particle* dst, uint32_t count);
  * (hg_host_alloc) for the copy to overlap. */
 int hg_upload_async(hg_ctx* ctx, int field, const float* src_rgba32f);
 int hg_download_async(hg_ctx* ctx, int field, float* dst_rgba32f);
+/* One Erosion::dispatch_grid (src/erosion.cpp:158-200) from HOST images to HOST images in the
+ * reference's texture format: uploads H, F, S (rows*map_w*4 floats each), steps, downloads
+ * H, F, S.  Asynchronous and pipelined over three streams: consecutive calls overlap their
+ * PCIe transfers in both directions with the step.  Neither inputs nor outputs may be
+ * touched before hg_sync; outputs of one call must not be inputs of the next (use two sets).
+ * Grid contexts on the FUSED schedule. */
+int hg_step_host_async(hg_ctx* ctx, const float* in_h, const float* in_f, const float* in_s,
+                       float* out_h, float* out_f, float* out_s);
 void* hg_host_alloc(size_t bytes);   /* pinned host memory */
 void hg_host_free(void* p);
 

@@ -247,3 +247,28 @@ def test_mass_and_roundtrip(built, wet256):
     np.testing.assert_allclose(ctx.mass(), want, rtol=1e-12)
     assert_bit_equal(ctx.download(0), H, "upload/download round trip")
     ctx.close()
+
+
+def test_step_host_async_pipelined(built, wet256):
+    """hg_step_host_async: host images in -> one fused step -> host images out, three calls in
+    flight back to back; every output equals the plain upload/dispatch/download result."""
+    from hydro_gen_b200 import PinnedBuffer
+    names = ("heightmap", "flux", "sediment")
+    ref_ctx = Context(256)
+    copy_state(wet256, ref_ctx)
+    ref_ctx.dispatch_grid()
+    want = [ref_ctx.download(FIELDS[n]) for n in names]
+    ctx = Context(256)
+    pins = [PinnedBuffer((256, 256, 4)) for _ in names]
+    outs = [[PinnedBuffer((256, 256, 4)) for _ in names] for _ in range(3)]
+    for p, n in zip(pins, names):
+        p.array[...] = wet256.get(FIELDS[n])
+    for k in range(3):
+        ctx.step_host_async([p.array for p in pins], [p.array for p in outs[k]])
+    ctx.sync()
+    for k in range(3):
+        for p, w_, n in zip(outs[k], want, names):
+            assert_bit_equal(p.array, w_, f"pipelined host step {k}: {n}")
+    for p in pins + [q for o in outs for q in o]:
+        p.free()
+    ctx.close(); ref_ctx.close()
