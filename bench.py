@@ -83,9 +83,12 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic():
-    """dram bytes per fused launch from the committed ncu summary of the same workload, or None."""
+    """dram bytes per fused launch from the newest committed ncu summary of the same workload
+    (profiles/rNN*_fused_step.json, written by scripts/ncu_summary.py), or None."""
+    import glob
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_fused_step.json")) as f:
+        path = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fused_step.json")))[-1]
+        with open(path) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except Exception:
         return None

@@ -20,6 +20,11 @@
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
 
+#ifndef HG_FREE_UNROLL
+#define HG_FREE_UNROLL 1
+#endif
+constexpr int kFreeUnroll = HG_FREE_UNROLL;
+
 namespace {
 
 struct FusedArgs {
@@ -37,71 +42,87 @@ struct FusedArgs {
 };
 
 // ------------------------------------------------------------------ far-fetch path
-__device__ __forceinline__ const float* far_plane(const FusedArgs& A, int plane, int gy, size_t* idx_row) {
+// Row gy of the pre-step plane set, wherever it lives: pointer to (plane 0, row gy, column 0)
+// and the plane stride of that slab.  The own slab (ghost rows included) is tried first; a row
+// outside it is read through the owning rank's peer pointer.  gy must be inside the map.
+struct FarRow { const float* p; size_t pe; };
+__device__ __forceinline__ FarRow far_row(const FusedArgs& A, int gy) {
     const HgSlabTable& T = A.slabs;
     int k = T.me;
     if (gy < T.row0[k] - HG_HALO_ROWS || gy >= T.row0[k] + T.rows[k] + HG_HALO_ROWS) {
         for (int j = 0; j < T.n; j++)
             if (gy >= T.row0[j] && gy < T.row0[j] + T.rows[j]) { k = j; break; }
     }
-    size_t pe = (size_t)(T.rows[k] + 2 * HG_HALO_ROWS) * A.pitch;
-    *idx_row = (size_t)(gy - T.row0[k] + HG_HALO_ROWS) * A.pitch;
-    return T.arena[k] + ((size_t)A.src_set[plane] * HG_NPLANES + plane) * pe;
+    FarRow r;
+    r.pe = (size_t)(T.rows[k] + 2 * HG_HALO_ROWS) * A.pitch;
+    r.p = T.arena[k] + (size_t)A.src_set[0] * HG_NPLANES * r.pe + (size_t)(gy - T.row0[k] + HG_HALO_ROWS) * A.pitch;
+    return r;
 }
-__device__ __forceinline__ float far_ld(const FusedArgs& A, int plane, int x, int gy, float oobv) {
-    if (x < 0 || x > A.W - 1 || gy < 0 || gy > A.H - 1) return oobv;
-    size_t r;
-    const float* p = far_plane(A, plane, gy, &r);
-    return __ldcg(p + r + x);
-}
-// Stage A of any in-map cell recomputed from the pre-step planes: S' and the velocity.
-// An out-of-map texel is texelFetch's 0.
-__device__ __noinline__ void far_stage_a(const FusedArgs& A, int x, int gy, float* sr, float* sd, float* u, float* v) {
-    if (x < 0 || x > A.W - 1 || gy < 0 || gy > A.H - 1) { *sr = 0.0f; *sd = 0.0f; *u = 0.0f; *v = 0.0f; return; }
-    float rk[5], dt[5], at[5];   // own, L, R, T, B
-    const int ox[5] = {0, -1, 1, 0, 0}, oy[5] = {0, 0, 0, 1, -1};
-    float water = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        int xx = x + ox[k], yy = gy + oy[k];
-        bool in = !(xx < 0 || xx > A.W - 1 || yy < 0 || yy > A.H - 1);
-        float r = far_ld(A, PL_ROCK, xx, yy, 0.0f), d = far_ld(A, PL_DIRT, xx, yy, 0.0f), w = far_ld(A, PL_WATER, xx, yy, 0.0f);
-        rk[k] = r; dt[k] = d;
-        at[k] = in ? r + d + w : HG_OOB_HEIGHT;
-        if (k == 0) water = w;
-    }
-    HgFluxOut o = hg_flux_cell(A.P, x, gy, A.W, A.H, at[0], at[1], at[2], at[3], at[4],
-        far_ld(A, PL_FL, x, gy, 0.0f), far_ld(A, PL_FR, x, gy, 0.0f), far_ld(A, PL_FT, x, gy, 0.0f), far_ld(A, PL_FB, x, gy, 0.0f),
-        far_ld(A, PL_FR, x - 1, gy, 0.0f), far_ld(A, PL_FL, x + 1, gy, 0.0f),
-        far_ld(A, PL_FB, x, gy + 1, 0.0f), far_ld(A, PL_FT, x, gy - 1, 0.0f), water);
-    HgEroOut e = hg_erosion_cell(A.P, rk[0], dt[0], far_ld(A, PL_SR, x, gy, 0.0f), far_ld(A, PL_SD, x, gy, 0.0f),
-        o.u, o.v, o.vz, rk[2], dt[2], rk[1], dt[1], rk[4], dt[4], rk[3], dt[3]);
-    *sr = e.sr; *sd = e.sd; *u = o.u; *v = o.v;
+// Stage A of any cell recomputed from the pre-step planes: S' and the velocity.  An out-of-map
+// texel is texelFetch's 0.  All 25 loads are issued from clamped (always valid) addresses before
+// any of them is used, and out-of-map neighbours are replaced afterwards, so one evaluation
+// costs one memory round trip.  (All nine read planes sit in the same ping-pong set: align_sets.)
+__device__ __forceinline__ void far_stage_a(const FusedArgs& A, int x, int gy, float* sr, float* sd, float* u, float* v) {
+    const bool inmap = !(x < 0 || x > A.W - 1 || gy < 0 || gy > A.H - 1);
+    const int cx = min(max(x, 0), A.W - 1), cy = min(max(gy, 0), A.H - 1);
+    const bool hasL = cx > 0, hasR = cx < A.W - 1, hasB = cy > 0, hasT = cy < A.H - 1;
+    const int xl = hasL ? cx - 1 : cx, xr = hasR ? cx + 1 : cx;
+    const FarRow r0 = far_row(A, cy), rt = far_row(A, hasT ? cy + 1 : cy), rb = far_row(A, hasB ? cy - 1 : cy);
+#define FL(row, plane, col) __ldcg((row).p + (size_t)(plane) * (row).pe + (col))
+    const float rk0 = FL(r0, PL_ROCK, cx), dt0 = FL(r0, PL_DIRT, cx), w0 = FL(r0, PL_WATER, cx);
+    float rkL = FL(r0, PL_ROCK, xl), dtL = FL(r0, PL_DIRT, xl), wL = FL(r0, PL_WATER, xl);
+    float rkR = FL(r0, PL_ROCK, xr), dtR = FL(r0, PL_DIRT, xr), wR = FL(r0, PL_WATER, xr);
+    float rkT = FL(rt, PL_ROCK, cx), dtT = FL(rt, PL_DIRT, cx), wT = FL(rt, PL_WATER, cx);
+    float rkB = FL(rb, PL_ROCK, cx), dtB = FL(rb, PL_DIRT, cx), wB = FL(rb, PL_WATER, cx);
+    const float fL = FL(r0, PL_FL, cx), fR = FL(r0, PL_FR, cx), fT = FL(r0, PL_FT, cx), fB = FL(r0, PL_FB, cx);
+    float inL = FL(r0, PL_FR, xl), inR = FL(r0, PL_FL, xr), inT = FL(rt, PL_FB, cx), inB = FL(rb, PL_FT, cx);
+    const float s0 = FL(r0, PL_SR, cx), s1 = FL(r0, PL_SD, cx);
+#undef FL
+    // H.a of the neighbours in the shader's association (r + g) + b; imageLoad outside the map: 0 / OOB height
+    float aL = rkL + dtL + wL, aR = rkR + dtR + wR, aT = rkT + dtT + wT, aB = rkB + dtB + wB;
+    if (!hasL) { rkL = 0.0f; dtL = 0.0f; aL = HG_OOB_HEIGHT; inL = 0.0f; }
+    if (!hasR) { rkR = 0.0f; dtR = 0.0f; aR = HG_OOB_HEIGHT; inR = 0.0f; }
+    if (!hasT) { rkT = 0.0f; dtT = 0.0f; aT = HG_OOB_HEIGHT; inT = 0.0f; }
+    if (!hasB) { rkB = 0.0f; dtB = 0.0f; aB = HG_OOB_HEIGHT; inB = 0.0f; }
+    HgFluxOut o = hg_flux_cell(A.P, cx, cy, A.W, A.H, rk0 + dt0 + w0, aL, aR, aT, aB, fL, fR, fT, fB, inL, inR, inT, inB, w0);
+    HgEroOut e = hg_erosion_cell(A.P, rk0, dt0, s0, s1, o.u, o.v, o.vz, rkR, dtR, rkL, dtL, rkB, dtB, rkT, dtT);
+    *sr = inmap ? e.sr : 0.0f; *sd = inmap ? e.sd : 0.0f; *u = inmap ? o.u : 0.0f; *v = inmap ? o.v : 0.0f;
 }
 
-// One thread per listed cell: the sediment pass of sediment_transport.glsl:66-93 with every
-// texel recomputed from pre-step state.
+// Four lanes per listed cell: the sediment pass of sediment_transport.glsl:66-93 with every
+// texel recomputed from pre-step state.  All four lanes evaluate the cell itself (same
+// addresses, one broadcast load each) to get its velocity and back-traced position, then lane q
+// evaluates texel (px + (q & 1), py + (q >> 1)) and lane 0 gathers the four by shuffle: two
+// memory round trips per cell instead of five dependent evaluations in one thread.
 __global__ void __launch_bounds__(128) k_far_fixup(const __grid_constant__ FusedArgs A) {
     const unsigned long long n = *A.far_count;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *A.far_count_next = 0ull;
         if (n) atomicAdd(A.far_total, n);
     }
-    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned li = A.far_list[e];
+    const int q = threadIdx.x & 3;
+    const unsigned long long stride = (unsigned long long)gridDim.x * (blockDim.x / 4);
+    const unsigned long long n_up = (n + 7ull) / 8ull * 8ull;      // whole warps stay in the loop together (shuffles)
+    for (unsigned long long e = blockIdx.x * (unsigned long long)(blockDim.x / 4) + threadIdx.x / 4; e < n_up; e += stride) {
+        const bool live = e < n;
+        unsigned li = live ? A.far_list[e] : 0u;
         int ly = (int)(li / (unsigned)A.W), x = (int)(li - (unsigned)ly * (unsigned)A.W);
         int gy = A.row0 + ly;
         float s0, s1, u, v;
         far_stage_a(A, x, gy, &s0, &s1, &u, &v);
         HgBack b = hg_backtrace(A.P, x, gy, A.W, A.H, u, v);
-        float t00r, t00d, t10r, t10d, t01r, t01d, t11r, t11d, du, dv;
-        far_stage_a(A, b.px, b.py, &t00r, &t00d, &du, &dv);
-        far_stage_a(A, b.px + 1, b.py, &t10r, &t10d, &du, &dv);
-        far_stage_a(A, b.px, b.py + 1, &t01r, &t01d, &du, &dv);
-        far_stage_a(A, b.px + 1, b.py + 1, &t11r, &t11d, &du, &dv);
-        size_t idx = (size_t)(ly + HG_HALO_ROWS) * A.pitch + x;
-        A.dst[PL_SR][idx] = hg_bilerp(t00r, t10r, t01r, t11r, b.sx, b.sy);
-        A.dst[PL_SD][idx] = hg_bilerp(t00d, t10d, t01d, t11d, b.sx, b.sy);
+        float tr, td, du, dv;
+        far_stage_a(A, b.px + (q & 1), b.py + (q >> 1), &tr, &td, &du, &dv);
+        const int base = (threadIdx.x & 31) & ~3;
+        const float t00r = __shfl_sync(0xffffffffu, tr, base), t10r = __shfl_sync(0xffffffffu, tr, base + 1);
+        const float t01r = __shfl_sync(0xffffffffu, tr, base + 2), t11r = __shfl_sync(0xffffffffu, tr, base + 3);
+        const float t00d = __shfl_sync(0xffffffffu, td, base), t10d = __shfl_sync(0xffffffffu, td, base + 1);
+        const float t01d = __shfl_sync(0xffffffffu, td, base + 2), t11d = __shfl_sync(0xffffffffu, td, base + 3);
+        if (live && q == 0) {
+            size_t idx = (size_t)(ly + HG_HALO_ROWS) * A.pitch + x;
+            A.dst[PL_SR][idx] = hg_bilerp(t00r, t10r, t01r, t11r, b.sx, b.sy);
+            A.dst[PL_SD][idx] = hg_bilerp(t00d, t10d, t01d, t11d, b.sx, b.sy);
+        }
     }
 }
 
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         __syncthreads();                                                                                             \
     }
     for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW(false)
-#pragma unroll 1
+#pragma unroll kFreeUnroll
     for (; i <= pl.free_hi; i++, off += pitch) HG_ROW(true)
     for (; i <= pl.i_end; i++, off += pitch) HG_ROW(false)
 #undef HG_ROW

@@ -11,8 +11,23 @@ struct HgFbm {
     bool turbulence, ridge;   // gln_tFBMOpts.terbulance / .ridge
 };
 
+// mod(x, 289) = x - 289*floor(x/289).  On the device the IEEE quotient comes from one multiply
+// and two FMAs (q = x*c; r = fma(-289, q, x); q + r*c with c = RN(1/289)), bit-identical to x/289
+// for every finite float (exhaustive proof: scripts/check_div_const.c); the host build keeps the
+// defining formula and the GPU parity tests compare the two.
+HG_FN float hg_mod289(float x) {
+#if HG_DEVICE_FAST
+    const float c = 1.0f / 289.0f;
+    const float q = __fmul_rn(x, c);
+    const float q2 = __fmaf_rn(__fmaf_rn(-289.0f, q, x), c, q);
+    return x - 289.0f * floorf(q2);
+#else
+    return hg_mod(x, 289.0f);
+#endif
+}
+
 // gln_rand3 == _permute: mod(((p*34)+1)*p, 289)      simplex_noise.glsl:320
-HG_FN float hg_permute(float p) { return hg_mod(((p * 34.0f) + 1.0f) * p, 289.0f); }
+HG_FN float hg_permute(float p) { return hg_mod289(((p * 34.0f) + 1.0f) * p); }
 
 // gln_simplex                                          simplex_noise.glsl:377-402
 HG_FN float hg_simplex(float vx, float vy) {
@@ -27,8 +42,8 @@ HG_FN float hg_simplex(float vx, float vy) {
     float x1x = x0x + Cx, x1y = x0y + Cx, x2x = x0x + Cz, x2y = x0y + Cz;
     x1x -= i1x;
     x1y -= i1y;
-    ix = hg_mod(ix, 289.0f);
-    iy = hg_mod(iy, 289.0f);
+    ix = hg_mod289(ix);
+    iy = hg_mod289(iy);
     float p0 = hg_permute(hg_permute(iy + 0.0f) + ix + 0.0f);
     float p1 = hg_permute(hg_permute(iy + i1y) + ix + i1x);
     float p2 = hg_permute(hg_permute(iy + 1.0f) + ix + 1.0f);
