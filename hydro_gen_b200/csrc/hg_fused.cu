@@ -219,6 +219,82 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
 #undef HG_ROW
 }
 
+// Warp-specialised form of the same step: a CTA of 2*NT threads, threads [0, NT) run the
+// hydraulic stages (L, A, B) of the strip's NT columns and threads [NT, 2*NT) the thermal and
+// smoothing stages (C..G) of the same columns, one row behind each other through the rings
+// (hg_fused_body.cuh).  The two groups rebalance the CTA's registers with setmaxnreg (RH for a
+// hydraulic thread, RT for a thermal one, (RH + RT) / 2 = the launch allocation), so three CTAs
+// = 24 warps stay resident per SM where the single-group kernel holds 16: the step is bound by
+// instruction issue and latency, not by HBM, and the extra warps are what hides the latency.
+template <int RH> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RH)); }
+template <int RT> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RT)); }
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+template <int NT, int MINB, int RH, int RT>
+__global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smb[];
+    float* const sm = smb + FusedSmem<NT>::RINGS;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
+    const bool hydro = threadIdx.x < NT;
+    const int tid = hydro ? threadIdx.x : threadIdx.x - NT;
+    const int strip = blockIdx.x % K.nstrips, segi = blockIdx.x / K.nstrips;
+    const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
+    const int x = x0 + tid;
+    const bool xin = x >= 0 && x < K.W;
+    const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
+    const int gy0 = K.row0 + segi * K.seg;
+    const int gy1 = min(gy0 + K.seg, K.row0 + K.rows);
+    const HgFusedPlan pl = hg_fused_plan(gy0, gy1, K.H);
+    const unsigned pitch = (unsigned)K.pitch;
+    unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
+    const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
+    constexpr unsigned BOX_BYTES = (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
+    const int bx0 = x0 - 2;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], BOX_BYTES);
+        tma_load_3d(smb, &tmap, &bars[0], bx0, ly0, 0);
+    }
+    __syncthreads();
+    HgCol c;
+    hg_fused_begin(c);
+    int i = pl.i_begin;
+    if (hydro) {
+        reg_dec<RH>();
+#define HG_ROW_H(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        const int rel = i - pl.i_begin;                                                                              \
+        if (tid == 0 && i < pl.i_end) {                                                                              \
+            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
+            tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
+        }                                                                                                            \
+        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#undef HG_ROW_H
+    } else {
+        reg_inc<RT>();
+#define HG_ROW_T(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        hg_fused_iter<NT, FREEFLAG, HGF_THERMAL>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#undef HG_ROW_T
+    }
+}
+
 }  // namespace
 
 // 3-D tensor map over one ping-pong set of the arena: (column, plane row, plane), box (NT+4) x 1 x 9.
@@ -264,6 +340,29 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
     k_fused_step<NT, MINB><<<K.nstrips * nseg, NT, smem, c->stream>>>(K, tmap);
+    HG_LAUNCH_CHECK(c);
+    if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
+    return HG_OK;
+}
+
+template <int NT, int MINB, int RH, int RT>
+static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
+    static_assert((RH + RT) / 2 * 2 * NT * MINB <= 65536 && RH % 8 == 0 && RT % 8 == 0, "register budget of the two warp groups");
+    HgFusedK K = K0;
+    K.nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
+    K.seg = seg;
+    int nseg = (c->g.rows + seg - 1) / seg;
+    constexpr size_t smem = FusedSmem<NT>::BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    alignas(64) CUtensorMap tmap;
+    int rc = make_tmap(c, src_set, NT, &tmap);
+    if (rc) return rc;
+    if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
+    k_fused_ws<NT, MINB, RH, RT><<<K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
@@ -315,9 +414,11 @@ int hg_launch_fused_step(hg_ctx* c) {
     c->far_parity ^= 1;
     A.P = K.P = c->sp;
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
-    static const int nt_of[] = {128, 128, 192, 224, 224};
-    static const int res_of[] = {4, 3, 2, 2, 1};
-    int v = c->tune_variant >= 0 && c->tune_variant < 5 ? c->tune_variant : 0;
+    // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA
+    static const int nt_of[] = {128, 128, 192, 224, 224, 128, 128, 128};
+    static const int res_of[] = {4, 3, 2, 2, 1, 3, 2, 3};
+    static const int wpc_of[] = {4, 4, 6, 7, 7, 8, 8, 8};
+    int v = c->tune_variant >= 0 && c->tune_variant < 8 ? c->tune_variant : 5;   // default: warp-specialised, 3 CTAs per SM
     const int NT = nt_of[v];
     int nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
     // Rows per CTA.  A CTA runs seg + 17 row iterations (pipeline fill), about 8 of them of the
@@ -326,7 +427,7 @@ int hg_launch_fused_step(hg_ctx* c) {
     // Pick the segment count that minimises the sum over the waves of this grid.
     int seg = c->tune_seg;
     if (seg <= 0) {
-        const int res = res_of[v], wpc = NT / 32;
+        const int res = res_of[v], wpc = wpc_of[v];
         double best = 1e30;
         for (int nseg = 1; nseg <= c->g.rows / 16 + 1 && nseg <= 4096; nseg++) {
             int sg = (c->g.rows + nseg - 1) / nseg;
@@ -344,7 +445,10 @@ int hg_launch_fused_step(hg_ctx* c) {
     case 1: rc = launch_main<128, 3>(c, K, seg, c->ri[0]); break;
     case 2: rc = launch_main<192, 2>(c, K, seg, c->ri[0]); break;
     case 3: rc = launch_main<224, 2>(c, K, seg, c->ri[0]); break;
-    default: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
+    case 4: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
+    case 5: rc = launch_ws<128, 3, 72, 88>(c, K, seg, c->ri[0]); break;
+    case 6: rc = launch_ws<128, 2, 96, 128>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_ws<128, 3, 64, 96>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);

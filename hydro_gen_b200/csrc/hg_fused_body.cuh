@@ -35,6 +35,13 @@
 //   R1D float2 (rock1, dirtE)                               after stage D      N=2
 //   G2  float2 (rock1, dirt2)                               after stage F      N=4
 //
+// Every hand-off between the hydraulic stages (L, A, B) and the thermal/smoothing stages (C..G)
+// already goes through a ring with a lag of at least one row: rockE via RE, dirtE via DE.  The
+// body can therefore be split between two warp groups of one CTA that share the rings and the
+// one barrier per row (GROUP = HGF_HYDRO / HGF_THERMAL, k_fused_ws): each group carries only its
+// own half of the column history, which halves the registers a thread needs and lets half as
+// many more warps stay resident.  GROUP = HGF_ALL is the single-group form (k_fused_step).
+//
 // This header is plain C++ apart from the HGF_* macros, so tests/host_emul runs the very
 // same body thread by thread on the CPU (-m "not gpu") against the oracle.
 #pragma once
@@ -48,6 +55,10 @@
 #define HGF_ATOMIC_INC64(p) ((*(p))++)
 #endif
 
+constexpr int HGF_ALL = 0, HGF_HYDRO = 1, HGF_THERMAL = 2;   // which stages a warp group runs
+#ifndef HGF_SMOOTH_GROUP
+#define HGF_SMOOTH_GROUP HGF_THERMAL
+#endif
 constexpr int HGF_HX = 6;        // halo columns per side
 constexpr int HGF_LAG_G = 11;    // rows between L and G
 constexpr int HGF_NPL = 9;       // rock dirt water fL fR fT fB sr sd (HgPlane order)
@@ -115,7 +126,7 @@ HG_FN void hg_col_init(HgCol& c) {
 // thread; xin/owned: column inside the map / inside the strip proper; gy0, gy1: the CTA's
 // row segment; off: element offset of (row i, column x) inside a plane.
 // FREE: see the header.
-template <int NT, bool FREE>
+template <int NT, bool FREE, int GROUP = HGF_ALL>
 HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
                          const int gy0, const int gy1, const int i, const unsigned off) {
     typedef HgRings<NT> R;
@@ -131,6 +142,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
 #define F2(ring, slot, el) f2[(ring) / 2 + (slot) * R::E + (el)]
 #define F1(ring, slot, el) sm[(ring) + (slot) * R::E + (el)]
 
+    if (GROUP != HGF_THERMAL) {
     // ------------------------------------------------------------ L(i)
     c.rk0 = c.rk1; c.rk1 = c.rk2; c.dt0 = c.dt1; c.dt1 = c.dt2; c.at0 = c.at1; c.at1 = c.at2; c.w1 = c.w2;
     c.f0T = c.f1T; c.f1L = c.f2L; c.f1R = c.f2R; c.f1T = c.f2T; c.f1B = c.f2B; c.s1r = c.s2r; c.s1d = c.s2d;
@@ -206,6 +218,10 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         }
     }
 
+    c.u_d2 = c.u_d1; c.v_d2 = c.v_d1; c.u_d1 = u_new; c.v_d1 = v_new;
+    }   // GROUP != HGF_THERMAL
+
+    if (GROUP != HGF_HYDRO) {
     // ------------------------------------------------------------ C(i-3), D(i-5)
     {
         const float rockE_d = c.e01;     // rockE of row i-5 leaves the window now; D needs it
@@ -293,8 +309,13 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         c.nRT1_d2 = c.nRT1_d1; c.nRT1_d1 = nl.y; c.nLT1_d2 = c.nLT1_d1; c.nLT1_d1 = nr.y;
     }
 
+    }   // GROUP != HGF_HYDRO
+
     // ------------------------------------------------------------ G(i-11)
-    {
+    // Smoothing reads only the G2 ring, so either group could run it.  The hydraulic group executes
+    // 20 % fewer instructions per row than the thermal group, but moving G there was measured 6 %
+    // slower (its instruction stream is the latency-heavy one: divisions, sqrt, the TMA wait).
+    if (GROUP == HGF_ALL || GROUP == HGF_SMOOTH_GROUP) {
         // own column of (rock1, dirt2): rows i-12, i-11, i-10 (row i-10 was written last iteration)
         const HgF2 own = F2(R::G2, SLOT(10, 4), e);
         c.g_r0 = c.g_r1; c.g_r1 = c.g_r2; c.g_r2 = own.x;
@@ -313,8 +334,6 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             }
         }
     }
-
-    c.u_d2 = c.u_d1; c.v_d2 = c.v_d1; c.u_d1 = u_new; c.v_d1 = v_new;
 #undef SLOT
 #undef F4
 #undef F2

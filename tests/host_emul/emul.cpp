@@ -119,8 +119,13 @@ void emul_rain(const hg_rain_data* set, const hg_map_settings_data* map_set, flo
 // barrier per row), with the same generic / FREE iteration plan as k_fused_step.
 // src/dst: 9 planes of W*H floats (no ghost rows).  far_out receives the local cell indices
 // whose sediment the kernel leaves to the far-fetch fix-up; returns their number.
+// ws = 0: one thread per column runs all stages (k_fused_step).  ws = 1 / 2: the warp-specialised
+// form (k_fused_ws): a hydraulic thread and a thermal thread per column, each with its own column
+// history; within an iteration all hydraulic threads run before all thermal threads (ws = 1) or
+// after them (ws = 2) -- on the GPU the two groups run concurrently between two barriers, so both
+// orders must give the same bits (any same-iteration hand-off through the rings would break one).
 template <int NT>
-static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, const float* const src[9], float* const dst[9], unsigned* far_out) {
+static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
     const int HALO = 8;
     size_t pe = (size_t)(H + 2 * HALO) * W;
     std::vector<std::vector<float>> ps(9, std::vector<float>(pe, 0.0f)), pd(9, std::vector<float>(pe, 0.0f));
@@ -135,7 +140,7 @@ static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, c
     K.P = hg_make_step_params(*set);
     int nseg = (H + seg - 1) / seg;
     std::vector<float> sm(HgRings<NT>::TOTAL + 4);
-    std::vector<HgCol> cols(NT);
+    std::vector<HgCol> cols(NT), colsT(NT);
     for (int blk = 0; blk < K.nstrips * nseg; blk++) {
         std::fill(sm.begin(), sm.end(), 0.0f);
         float* smp = sm.data();
@@ -145,7 +150,7 @@ static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, c
         HgFusedPlan pl = hg_fused_plan(gy0, gy1, H);
         auto xof = [&](int tid) { return strip * (NT - 12) - 6 + tid; };
         auto offof = [&](int tid, int i) { return (unsigned)(i + HALO) * (unsigned)W + (unsigned)xof(tid); };
-        for (int tid = 0; tid < NT; tid++) hg_fused_begin(cols[tid]);
+        for (int tid = 0; tid < NT; tid++) { hg_fused_begin(cols[tid]); hg_fused_begin(colsT[tid]); }
         std::vector<float> raw(9 * HGF_RAW_LD(NT));
         for (int i = pl.i_begin; i <= pl.i_end; i++) {
             bool fr = i >= pl.free_lo && i <= pl.free_hi;
@@ -154,22 +159,35 @@ static long fused_step_emul(const hg_erosion_data* set, int W, int H, int seg, c
                 int x = xof(0) - 2 + t, lr = i + HALO;
                 raw[p * HGF_RAW_LD(NT) + t] = (x >= 0 && x < W && lr >= 0 && lr < H + 2 * HALO) ? ps[p][(size_t)lr * W + x] : 0.0f;
             }
-            for (int tid = 0; tid < NT; tid++) {
-                int x = xof(tid);
-                bool xin = x >= 0 && x < W, owned = tid >= 6 && tid < NT - 6 && x < W;
-                unsigned off = offof(tid, i);
-                if (fr) hg_fused_iter<NT, true>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
-                else hg_fused_iter<NT, false>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
-            }
+            auto run_group = [&](int group) {
+                for (int tid = 0; tid < NT; tid++) {
+                    int x = xof(tid);
+                    bool xin = x >= 0 && x < W, owned = tid >= 6 && tid < NT - 6 && x < W;
+                    unsigned off = offof(tid, i);
+                    if (group == HGF_ALL) {
+                        if (fr) hg_fused_iter<NT, true>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                        else hg_fused_iter<NT, false>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                    } else if (group == HGF_HYDRO) {
+                        if (fr) hg_fused_iter<NT, true, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                        else hg_fused_iter<NT, false, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                    } else {
+                        if (fr) hg_fused_iter<NT, true, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                        else hg_fused_iter<NT, false, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, off);
+                    }
+                }
+            };
+            if (ws == 0) run_group(HGF_ALL);
+            else if (ws == 1) { run_group(HGF_HYDRO); run_group(HGF_THERMAL); }
+            else { run_group(HGF_THERMAL); run_group(HGF_HYDRO); }
         }
     }
     for (int p = 0; p < 9; p++) memcpy(dst[p], pd[p].data() + (size_t)HALO * W, (size_t)W * H * 4);
     return (long)far_count;
 }
 
-extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt, int seg, const float* const src[9], float* const dst[9], unsigned* far_out) {
-    if (nt == 32) return fused_step_emul<32>(set, W, H, seg, src, dst, far_out);
-    if (nt == 128) return fused_step_emul<128>(set, W, H, seg, src, dst, far_out);
-    if (nt == 224) return fused_step_emul<224>(set, W, H, seg, src, dst, far_out);
+extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    if (nt == 32) return fused_step_emul<32>(set, W, H, seg, ws, src, dst, far_out);
+    if (nt == 128) return fused_step_emul<128>(set, W, H, seg, ws, src, dst, far_out);
+    if (nt == 224) return fused_step_emul<224>(set, W, H, seg, ws, src, dst, far_out);
     return -1;
 }

@@ -139,7 +139,7 @@ def test_struct_layouts_match_the_reference():
     assert oracle.PARTICLE_DTYPE.fields["sediment"][1] == 32 and oracle.PARTICLE_DTYPE.fields["to_kill"][1] == 40
 
 
-def fused_emul_step(E, w, nt, seg):
+def fused_emul_step(E, w, nt, seg, ws=0):
     """one step of the fused kernel body on the CPU; returns (planes, far cell indices)"""
     src = planes_of(w)
     dst = [np.zeros_like(p) for p in src]
@@ -148,23 +148,24 @@ def fused_emul_step(E, w, nt, seg):
     da = (C.c_void_p * 9)(*[p.ctypes.data for p in dst])
     er = hl.ErosionData.from_buffer_copy(bytes(w.erosion))
     E.emul_fused_step.restype = C.c_long
-    n = E.emul_fused_step(C.byref(er), w.W, w.H, nt, seg, sa, da, far.ctypes.data_as(C.c_void_p))
+    n = E.emul_fused_step(C.byref(er), w.W, w.H, nt, seg, ws, sa, da, far.ctypes.data_as(C.c_void_p))
     assert n >= 0
     return dst, far[:n]
 
 
-@pytest.mark.parametrize("nt,seg,shape", [(32, 16, (72, 64)), (32, 64, (40, 136)), (128, 32, (192, 96)), (128, 128, (128, 160)), (224, 64, (264, 80))])
-def test_fused_kernel_body_emulated_matches_oracle(emul, nt, seg, shape):
+@pytest.mark.parametrize("nt,seg,shape,ws", [(32, 16, (72, 64), 0), (32, 64, (40, 136), 0), (128, 32, (192, 96), 0), (128, 128, (128, 160), 0), (224, 64, (264, 80), 0),
+                                             (32, 16, (72, 64), 1), (32, 16, (72, 64), 2), (128, 32, (192, 96), 1), (128, 128, (128, 160), 2)])
+def test_fused_kernel_body_emulated_matches_oracle(emul, nt, seg, shape, ws):
     """hg_fused_body.cuh — the code k_fused_step runs — executed thread by thread on the CPU with
-    the kernel's own iteration plan (generic fill/drain + 6x unrolled FREE blocks), against the
-    oracle: every plane bit-exact; the cells it defers to the far-fetch fix-up are exactly the
+    the kernel's own iteration plan (generic fill/drain + FREE steady state), against the oracle;
+    ws = 1, 2: the warp-specialised split (k_fused_ws) with the two groups in either order: every plane bit-exact; the cells it defers to the far-fetch fix-up are exactly the
     cells whose back-trace leaves the +-1 window."""
     W, H = shape
     w = wet_world(H, 120, width=W, period=8)
     names = "rock dirt water fL fR fT fB sed_r sed_d".split()
     total_far = 0
     for _ in range(3):
-        got, far = fused_emul_step(emul, w, nt, seg)
+        got, far = fused_emul_step(emul, w, nt, seg, ws)
         pl = planes_of(w)
         far_ref = emul_step(emul, w, pl)            # the unfused emulation counts the same cells
         w.step((w.steps + 1) * DT_TIME)
