@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     hg_fused_begin(c);
     int i = pl.i_begin;
     if (hydro) {
-        reg_dec<RH>();
+        if (RH != RT) reg_dec<RH>();
 #define HG_ROW_H(FREEFLAG)                                                                                           \
     {                                                                                                                \
         const int rel = i - pl.i_begin;                                                                              \
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
 #undef HG_ROW_H
     } else {
-        reg_inc<RT>();
+        if (RH != RT) reg_inc<RT>();
 #define HG_ROW_T(FREEFLAG)                                                                                           \
     {                                                                                                                \
         hg_fused_iter<NT, FREEFLAG, HGF_THERMAL>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
@@ -415,10 +415,10 @@ int hg_launch_fused_step(hg_ctx* c) {
     A.P = K.P = c->sp;
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
     // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA
-    static const int nt_of[] = {128, 128, 192, 224, 224, 128, 128, 128};
-    static const int res_of[] = {4, 3, 2, 2, 1, 3, 2, 3};
-    static const int wpc_of[] = {4, 4, 6, 7, 7, 8, 8, 8};
-    int v = c->tune_variant >= 0 && c->tune_variant < 8 ? c->tune_variant : 5;   // default: warp-specialised, 3 CTAs per SM
+    static const int nt_of[] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128};
+    static const int res_of[] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4};
+    static const int wpc_of[] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8};
+    int v = c->tune_variant >= 0 && c->tune_variant < 10 ? c->tune_variant : 5;   // default: warp-specialised, 3 CTAs per SM
     const int NT = nt_of[v];
     int nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
     // Rows per CTA.  A CTA runs seg + 17 row iterations (pipeline fill), about 8 of them of the
@@ -448,7 +448,9 @@ int hg_launch_fused_step(hg_ctx* c) {
     case 4: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
     case 5: rc = launch_ws<128, 3, 72, 88>(c, K, seg, c->ri[0]); break;
     case 6: rc = launch_ws<128, 2, 96, 128>(c, K, seg, c->ri[0]); break;
-    default: rc = launch_ws<128, 3, 64, 96>(c, K, seg, c->ri[0]); break;
+    case 7: rc = launch_ws<128, 3, 64, 96>(c, K, seg, c->ri[0]); break;
+    case 8: rc = launch_ws<128, 4, 64, 64>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_ws<128, 4, 56, 72>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);

@@ -15,10 +15,13 @@
 //   F(i-9)  thermal transport, layer 1                  -> dirt2
 //   G(i-11) smoothing                                   -> rock', dirt' to HBM
 //
-// A thread keeps its own column's history in registers (HgCol); values of the x+-1
-// columns come through shared-memory row rings written at least one iteration earlier, so
-// ONE barrier per row is enough and the seven stages of an iteration are independent
-// instruction streams.  Ring rows are indexed by (absolute row mod N), N a power of two.
+// A thread keeps the history of the raw row, the velocity and the outflow sums of its own
+// column in registers (HgCol); values of the x+-1 columns come through shared-memory row rings
+// written at least one iteration earlier, so ONE barrier per row is enough and the seven stages
+// of an iteration are independent instruction streams.  The 3x3 windows of the thermal and
+// smoothing stages (rockE; rock1/dirtE; rock1/dirt2) are NOT held in registers: their rings are
+// four rows deep and the nine texels are re-read every row, which costs no more instructions than
+// rotating a register window (3 loads + 6 moves) and frees 33 registers per thread.  Ring rows are indexed by (absolute row mod N), N a power of two.
 // FREE=true is the steady state: every stage's row lies inside its active range and
 // strictly inside the map in y, so no range or y-border test is left; pipeline fill/drain
 // and the rows next to the map border use FREE=false, which tests everything.  The
@@ -28,11 +31,11 @@
 //
 // Exchanges are packed so one LDS/STS moves what a neighbour needs:
 //   XQ  float4 (H.a, rock, dirt, fR)   XL float fL          raw row            N=2
-//   RE  float  rockE                                        after stage A      N=2
+//   RE  float  rockE                                        after stage A      N=4
 //   DE  float  dirtE (own column only, A -> D)                                 N=8
 //   SS  float2 (S'.rock, S'.dirt)                           after stage A      N=4
 //   OxR float4 (R, RT, RB, -)  OxL float4 (L, LT, LB, -)    thermal outflow    N=2, per layer
-//   R1D float2 (rock1, dirtE)                               after stage D      N=2
+//   R1D float2 (rock1, dirtE)                               after stage D      N=4
 //   G2  float2 (rock1, dirt2)                               after stage F      N=4
 //
 // Every hand-off between the hydraulic stages (L, A, B) and the thermal/smoothing stages (C..G)
@@ -80,12 +83,12 @@ template <int NT> struct HgRings {
     static constexpr int O1R = O0L + 2 * E * 4;
     static constexpr int O1L = O1R + 2 * E * 4;
     static constexpr int SS = O1L + 2 * E * 4;      // float2 [4][E]
-    static constexpr int R1D = SS + 4 * E * 2;      // float2 [2][E]
-    static constexpr int G2 = R1D + 2 * E * 2;      // float2 [4][E]
+    static constexpr int R1D = SS + 4 * E * 2;      // float2 [4][E]
+    static constexpr int G2 = R1D + 4 * E * 2;      // float2 [4][E]
     static constexpr int XL = G2 + 4 * E * 2;       // float  [2][E]
-    static constexpr int RE = XL + 2 * E;           // float  [2][E]
-    static constexpr int DE = RE + 2 * E;           // float  [8][E]
-    static constexpr int TOTAL = DE + 8 * E;        // 72 * E floats
+    static constexpr int RE = XL + 2 * E;           // float  [4][E]
+    static constexpr int DE = RE + 4 * E;           // float  [8][E]
+    static constexpr int TOTAL = DE + 8 * E;        // 78 * E floats
 };
 
 struct HgFusedK {
@@ -106,14 +109,12 @@ struct HgCol {
     float f1L, f1R, f1T, f1B, f2L, f2R, f2T, f2B, f0T;
     float s1r, s1d, s2r, s2d;
     float u_d1, v_d1, u_d2, v_d2;                // velocity delayed 1, 2 iterations
-    float e00, e01, e02, e10, e11, e12, e20, e21, e22;   // rockE rows i-4..i-2, columns x-1..x+1
+    float e_old;                                 // own rockE of row i-5 (stage D)
     float so0_d1, so0_d2, T0_d1, T0_d2, T0_d3, B0_d1;
     float nR0_d1, nL0_d1, nRT0_d1, nRT0_d2, nLT0_d1, nLT0_d2;
-    float p00, p01, p02, p10, p11, p12, p20, p21, p22;   // rock1 rows i-8..i-6
-    float q00, q01, q02, q10, q11, q12, q20, q21, q22;   // dirtE rows i-8..i-6
+    float p_old, q_old;                          // own (rock1, dirtE) of row i-9 (stage F)
     float so1_d1, so1_d2, T1_d1, T1_d2, T1_d3, B1_d1;
     float nR1_d1, nL1_d1, nRT1_d1, nRT1_d2, nLT1_d1, nLT1_d2;
-    float g_r0, g_r1, g_r2, g_d0, g_d1, g_d2;    // own column of (rock1, dirt2) rows i-12..i-10
 };
 
 HG_FN void hg_col_init(HgCol& c) {
@@ -184,7 +185,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 K.dst[5][idx] = o.fT; K.dst[6][idx] = o.fB;
                 K.dst[2][idx] = o.water * P.evap;     // sediment_transport.glsl:75
             }
-            F1(R::RE, SLOT(1, 2), e) = in ? er.rock : HG_OOB_HEIGHT;
+            F1(R::RE, SLOT(1, 4), e) = in ? er.rock : HG_OOB_HEIGHT;
             F1(R::DE, SLOT(1, 8), e) = in ? er.dirt : HG_OOB_HEIGHT;
             HgF2 s; s.x = in ? er.sr : 0.0f; s.y = in ? er.sd : 0.0f;
             F2(R::SS, SLOT(1, 4), e) = s;
@@ -224,9 +225,13 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     if (GROUP != HGF_HYDRO) {
     // ------------------------------------------------------------ C(i-3), D(i-5)
     {
-        const float rockE_d = c.e01;     // rockE of row i-5 leaves the window now; D needs it
-        c.e00 = c.e10; c.e01 = c.e11; c.e02 = c.e12; c.e10 = c.e20; c.e11 = c.e21; c.e12 = c.e22;
-        c.e20 = F1(R::RE, SLOT(2, 2), e - 1); c.e21 = F1(R::RE, SLOT(2, 2), e); c.e22 = F1(R::RE, SLOT(2, 2), e + 1);
+        // rockE window: rows i-4 (y-1), i-3 (y), i-2 (y+1), columns x-1..x+1, straight from the ring
+        // (stage A writes row i-1 into the fourth slot meanwhile)
+        const float e00 = F1(R::RE, SLOT(4, 4), e - 1), e01 = F1(R::RE, SLOT(4, 4), e), e02 = F1(R::RE, SLOT(4, 4), e + 1);
+        const float e10 = F1(R::RE, SLOT(3, 4), e - 1), e11 = F1(R::RE, SLOT(3, 4), e), e12 = F1(R::RE, SLOT(3, 4), e + 1);
+        const float e20 = F1(R::RE, SLOT(2, 4), e - 1), e21 = F1(R::RE, SLOT(2, 4), e), e22 = F1(R::RE, SLOT(2, 4), e + 1);
+        const float rockE_d = c.e_old;   // own rockE of row i-5: last iteration's row y-1; D needs it
+        c.e_old = e01;
         const int yc = i - 3;
         float so0 = 0.0f, T0 = 0.0f, B0 = 0.0f;
         if (FREE || (yc >= gy0 - 4 && yc < gy1 + 4)) {
@@ -234,13 +239,13 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             float out[8], d_h[8];
             // L R T B LT RT LB RB; window rows: 0 = y-1, 1 = y, 2 = y+1.  The shader's "0 +" is
             // dropped: it can only turn a -0 difference into +0, and a zero d_h is never marked.
-            d_h[0] = c.e11 - c.e10; d_h[1] = c.e11 - c.e12; d_h[2] = c.e11 - c.e21; d_h[3] = c.e11 - c.e01;
-            d_h[4] = c.e11 - c.e20; d_h[5] = c.e11 - c.e22; d_h[6] = c.e11 - c.e00; d_h[7] = c.e11 - c.e02;
+            d_h[0] = e11 - e10; d_h[1] = e11 - e12; d_h[2] = e11 - e21; d_h[3] = e11 - e01;
+            d_h[4] = e11 - e20; d_h[5] = e11 - e22; d_h[6] = e11 - e00; d_h[7] = e11 - e02;
             if (!in) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) d_h[k] = -1.0f;   // an out-of-map cell has no outflow
             }
-            so0 = hg_thermal_outflow(P, 0, c.e11, d_h, out);
+            so0 = hg_thermal_outflow(P, 0, e11, d_h, out);
             T0 = out[2]; B0 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;    // R, RT, RB
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;    // L, LT, LB
@@ -255,7 +260,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             const bool in = xin && (FREE || (yd >= 0 && yd < H));
             float delta = hg_thermal_delta(c.so0_d2, c.nR0_d1, c.nL0_d1, c.B0_d1, c.T0_d3, nl.z, nr.z, c.nRT0_d2, c.nLT0_d2);
             HgF2 w; w.x = in ? rockE_d + delta : HG_OOB_HEIGHT; w.y = F1(R::DE, SLOT(5, 8), e);
-            F2(R::R1D, SLOT(5, 2), e) = w;
+            F2(R::R1D, SLOT(5, 4), e) = w;
         }
         c.so0_d2 = c.so0_d1; c.so0_d1 = so0;
         c.T0_d3 = c.T0_d2; c.T0_d2 = c.T0_d1; c.T0_d1 = T0;
@@ -266,27 +271,27 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
 
     // ------------------------------------------------------------ E(i-7), F(i-9)
     {
-        const float rock1_d = c.p01, dirtE_d = c.q01;     // (rock1, dirtE) of row i-9
-        c.p00 = c.p10; c.p01 = c.p11; c.p02 = c.p12; c.p10 = c.p20; c.p11 = c.p21; c.p12 = c.p22;
-        c.q00 = c.q10; c.q01 = c.q11; c.q02 = c.q12; c.q10 = c.q20; c.q11 = c.q21; c.q12 = c.q22;
-        {
-            const HgF2 a = F2(R::R1D, SLOT(6, 2), e - 1), b = F2(R::R1D, SLOT(6, 2), e), d = F2(R::R1D, SLOT(6, 2), e + 1);
-            c.p20 = a.x; c.q20 = a.y; c.p21 = b.x; c.q21 = b.y; c.p22 = d.x; c.q22 = d.y;
-        }
+        // (rock1, dirtE) window: rows i-8 (y-1), i-7 (y), i-6 (y+1), columns x-1..x+1, from the ring
+        // (stage D writes row i-5 into the fourth slot meanwhile)
+        const HgF2 w00 = F2(R::R1D, SLOT(8, 4), e - 1), w01 = F2(R::R1D, SLOT(8, 4), e), w02 = F2(R::R1D, SLOT(8, 4), e + 1);
+        const HgF2 w10 = F2(R::R1D, SLOT(7, 4), e - 1), w11 = F2(R::R1D, SLOT(7, 4), e), w12 = F2(R::R1D, SLOT(7, 4), e + 1);
+        const HgF2 w20 = F2(R::R1D, SLOT(6, 4), e - 1), w21 = F2(R::R1D, SLOT(6, 4), e), w22 = F2(R::R1D, SLOT(6, 4), e + 1);
+        const float rock1_d = c.p_old, dirtE_d = c.q_old;     // own (rock1, dirtE) of row i-9: last iteration's row y-1
+        c.p_old = w01.x; c.q_old = w01.y;
         const int ye = i - 7;
         float so1 = 0.0f, T1 = 0.0f, B1 = 0.0f;
         if (FREE || (ye >= gy0 - 2 && ye < gy1 + 2)) {
             const bool in = xin && (FREE || (ye >= 0 && ye < H));
             float out[8], d_h[8];
-            d_h[0] = (c.p11 - c.p10) + (c.q11 - c.q10); d_h[1] = (c.p11 - c.p12) + (c.q11 - c.q12);
-            d_h[2] = (c.p11 - c.p21) + (c.q11 - c.q21); d_h[3] = (c.p11 - c.p01) + (c.q11 - c.q01);
-            d_h[4] = (c.p11 - c.p20) + (c.q11 - c.q20); d_h[5] = (c.p11 - c.p22) + (c.q11 - c.q22);
-            d_h[6] = (c.p11 - c.p00) + (c.q11 - c.q00); d_h[7] = (c.p11 - c.p02) + (c.q11 - c.q02);
+            d_h[0] = (w11.x - w10.x) + (w11.y - w10.y); d_h[1] = (w11.x - w12.x) + (w11.y - w12.y);
+            d_h[2] = (w11.x - w21.x) + (w11.y - w21.y); d_h[3] = (w11.x - w01.x) + (w11.y - w01.y);
+            d_h[4] = (w11.x - w20.x) + (w11.y - w20.y); d_h[5] = (w11.x - w22.x) + (w11.y - w22.y);
+            d_h[6] = (w11.x - w00.x) + (w11.y - w00.y); d_h[7] = (w11.x - w02.x) + (w11.y - w02.y);
             if (!in) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) d_h[k] = -1.0f;
             }
-            so1 = hg_thermal_outflow(P, 1, c.q11, d_h, out);
+            so1 = hg_thermal_outflow(P, 1, w11.y, d_h, out);
             T1 = out[2]; B1 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;
@@ -316,16 +321,14 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     // 20 % fewer instructions per row than the thermal group, but moving G there was measured 6 %
     // slower (its instruction stream is the latency-heavy one: divisions, sqrt, the TMA wait).
     if (GROUP == HGF_ALL || GROUP == HGF_SMOOTH_GROUP) {
-        // own column of (rock1, dirt2): rows i-12, i-11, i-10 (row i-10 was written last iteration)
-        const HgF2 own = F2(R::G2, SLOT(10, 4), e);
-        c.g_r0 = c.g_r1; c.g_r1 = c.g_r2; c.g_r2 = own.x;
-        c.g_d0 = c.g_d1; c.g_d1 = c.g_d2; c.g_d2 = own.y;
+        // own column of (rock1, dirt2): rows i-12 (y-1), i-11 (y), i-10 (y+1); stage F writes row i-9 meanwhile
         const int yg = i - HGF_LAG_G;
         if (FREE || (yg >= gy0 && yg < gy1)) {
             const HgF2 l = F2(R::G2, SLOT(11, 4), e - 1), r = F2(R::G2, SLOT(11, 4), e + 1);
-            float rock = c.g_r1, dirt = c.g_d1;
+            const HgF2 dn = F2(R::G2, SLOT(12, 4), e), own = F2(R::G2, SLOT(11, 4), e), up = F2(R::G2, SLOT(10, 4), e);
+            float rock = own.x, dirt = own.y;
             float sr_ = rock, sd_ = dirt;
-            hg_smooth_cell(P, sr_, sd_, l.x, l.y, r.x, r.y, c.g_r2, c.g_d2, c.g_r0, c.g_d0);
+            hg_smooth_cell(P, sr_, sd_, l.x, l.y, r.x, r.y, up.x, up.y, dn.x, dn.y);
             const bool border = (x == 0 || x == W - 1 || (!FREE && (yg == 0 || yg == H - 1)));
             if (owned) {
                 const unsigned idx = off - (unsigned)HGF_LAG_G * pitch;
