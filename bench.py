@@ -227,7 +227,7 @@ def main():
     peak, peak_src = read_peak()
     achieved = ALG_BYTES_PER_CELL * W * rows / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_fused_step", "kernel_ms": k_ms, "peak_source": peak_src,
+                "traffic": ncu_traffic(), "kernel": "k_fused_ws", "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell_step": ALG_BYTES_PER_CELL, "cells_per_launch": W * rows,
                 "note": "the kernel is fp32-issue bound, not HBM bound (DESIGN.md §Roofline)"}
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches.csv")
 rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "fused_full.ncu-rep")
-kern = sys.argv[4] if len(sys.argv) > 4 else "fused_step"
+kern = sys.argv[4] if len(sys.argv) > 4 else "k_fused"      # k_fused_step (one warp group) or k_fused_ws (two)
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 
 if os.path.exists(launches):
@@ -58,7 +58,7 @@ if os.path.exists(rep):
             "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
             "smsp__thread_inst_executed_per_inst_executed.ratio", "sass__inst_executed_shared_loads", "sass__inst_executed_shared_stores",
             "sass__inst_executed_global_loads", "sass__inst_executed_global_stores", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-    name = re.sub(r"\W+", "_", kern)
+    name = "fused_step" if kern == "k_fused" else re.sub(r"\W+", "_", kern)
     with open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on, one launch of {row[hdr.index('Kernel Name')]}\n")
         for k in keys:
