@@ -7,6 +7,9 @@
 //
 //   hydro-gen-headless [--config config.ini] [--steps 500] [--seed 1234.5] [--dt 0.015]
 //                      [--rain-period N] [--no-rain] [--device 0] [--dump prefix]
+//                      [--resume file.hgck] [--checkpoint file.hgck]
+// --resume loads fields, settings and the step counter from a checkpoint (hg_checkpoint_load)
+// instead of generating a heightmap; --checkpoint writes one after the last step.
 #include <cctype>
 #include <cstring>
 #include <fstream>
@@ -65,7 +68,7 @@ const char* DEFAULT_CONFIG =          // src/main.cpp:206-216
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string config = "config.ini", dump;
+    std::string config = "config.ini", dump, resume, checkpoint;
     u32 steps = 500;
     float seed = 1234.5f, dt = 0.015f;
     int device = 0, rain_period = -1;
@@ -81,6 +84,8 @@ int main(int argc, char** argv) {
         else if (a == "--rain-period") rain_period = std::atoi(next());
         else if (a == "--no-rain") no_rain = true;
         else if (a == "--dump") dump = next();
+        else if (a == "--resume") resume = next();
+        else if (a == "--checkpoint") checkpoint = next();
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
 
@@ -108,11 +113,20 @@ int main(int argc, char** argv) {
     State::World::Textures world_data = State::World::gen_textures(MAP_SIZE, particle_count, device);
     State::World::gen_heightmap(settings, world_data, comput_map);
     Erosion::Programs* erosion_progs = Erosion::setup_shaders(erosion_type, settings, world_data, particle_count);
+    u32 step0 = 0;
+    if (!resume.empty()) {                           // fields, the three settings structs and the step counter
+        hydrogen_detail::check(hg_checkpoint_load(world_data.ctx, resume.c_str()), "hg_checkpoint_load");
+        hg_get_erosion(world_data.ctx, &settings.erosion.data);
+        hg_get_rain(world_data.ctx, &settings.rain.data);
+        hg_get_map(world_data.ctx, &settings.map.data);
+        hg_get_steps(world_data.ctx, &step0);
+        state.erosion_steps = step0;
+    }
 
     hg_sync(world_data.ctx);
     hg_timer_start(world_data.ctx);
     for (u32 k = 0; k < steps; k++) {                // main.cpp:310-324
-        world_data.time = (float)(k + 1) * dt;
+        world_data.time = (float)(step0 + k + 1) * dt;
         state.erosion_steps++;
         if (erosion_type == Erosion::Programs::GRID) {
             if (state.should_rain) {
@@ -131,6 +145,10 @@ int main(int argc, char** argv) {
                 erosion_type == Erosion::Programs::GRID ? "grid" : "particle", MAP_SIZE, MAP_SIZE, steps, ms / (steps ? steps : 1),
                 steps ? (double)MAP_SIZE * MAP_SIZE * steps / (ms * 1e-3) / 1e9 : 0.0, (unsigned long long)hg_launch_count(world_data.ctx));
     std::printf("mass: rock %.6f dirt %.6f water %.6f sediment %.6f %.6f\n", mass[0], mass[1], mass[2], mass[3], mass[4]);
+    if (!checkpoint.empty()) {
+        hg_set_steps(world_data.ctx, state.erosion_steps);
+        hydrogen_detail::check(hg_checkpoint_save(world_data.ctx, checkpoint.c_str()), "hg_checkpoint_save");
+    }
     if (!dump.empty()) {                             // raw little-endian RGBA32F, one file per renderer input
         const int fields[2] = {HG_FIELD_HEIGHTMAP, HG_FIELD_SEDIMENT};
         const char* names[2] = {"heightmap", "sediment"};

@@ -87,6 +87,8 @@ SYMBOLS = {
     "hg_upload_particles": (_i, [_vp, _vp, _u]),
     "hg_download_particles": (_i, [_vp, _vp, _u]),
     "hg_step_host_async": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hg_checkpoint_save": (_i, [_vp, C.c_char_p]),
+    "hg_checkpoint_load": (_i, [_vp, C.c_char_p]),
     "hg_host_alloc": (_vp, [C.c_size_t]),
     "hg_host_free": (None, [_vp]),
     "hg_mass": (_i, [_vp, C.POINTER(C.c_double)]),

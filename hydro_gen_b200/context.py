@@ -190,6 +190,13 @@ class Context:
     def slab_errors(self):
         v = C.c_uint64(); check(self.L.hg_slab_errors(self.h, C.byref(v))); return v.value
 
+    # ---- checkpoint (hg_checkpoint.cu; hydro_gen_b200.checkpoint reads the files without a GPU)
+    def save_checkpoint(self, path):
+        check(self.L.hg_checkpoint_save(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        check(self.L.hg_checkpoint_load(self.h, str(path).encode()))
+
     # ---- slabs
     def export_handle(self):
         e = SlabExport(); check(self.L.hg_slab_export_handle(self.h, C.byref(e))); return e

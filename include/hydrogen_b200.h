@@ -132,6 +132,17 @@ void hg_host_free(void* p);
  * mass diagnostic of the 1000-step drift test.  Blocking. */
 int hg_mass(hg_ctx* ctx, double out5[5]);
 
+/* ---- checkpoint (no counterpart in the reference: its fields live in GL textures and are lost
+ *      at exit, src/main.cpp:334-345).  One file holds the settings structs (byte images of
+ *      bindings.glsl:39-99), the step counter that drives the rain schedule (src/main.cpp:315-319),
+ *      the slab's fields as RGBA32F little-endian images (grid: heightmap, flux, sediment;
+ *      particles: heightmap, momentum map) and the droplet SSBO; layout in
+ *      hydro_gen_b200/csrc/hg_checkpoint.cu, reader/writer in hydro_gen_b200/checkpoint.py.
+ *      A run resumed from it continues bit for bit.  Load needs a context of the same geometry
+ *      and mode.  Blocking. ---- */
+int hg_checkpoint_save(hg_ctx* ctx, const char* path);
+int hg_checkpoint_load(hg_ctx* ctx, const char* path);
+
 /* ---- streams, sync, timing ---- */
 int hg_sync(hg_ctx* ctx);
 int hg_set_stream(hg_ctx* ctx, void* cuda_stream);   /* run on the caller's cudaStream_t */

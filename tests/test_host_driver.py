@@ -54,3 +54,20 @@ def test_headless_driver_matches_python_mirror(exe, tmp_path):
         got = np.fromfile(tmp_path / f"out.{name}.rgba32f", dtype=np.float32).reshape(256, 256, 4)
         assert np.array_equal(got.view(np.uint32), ctx.download(field).view(np.uint32)), name
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_headless_driver_resume_from_checkpoint(exe, tmp_path):
+    """40 steps in one go == 25 steps + --checkpoint, then --resume + 15 steps (fields bit for bit)."""
+    (tmp_path / "config.ini").write_text("[map]\nsize = 128\n[erosion]\ntype = grid\n")
+    common = ["--seed", "1234.5", "--rain-period", "8"]
+    r = subprocess.run([exe, "--steps", "40", "--dump", "full"] + common, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "--steps", "25", "--checkpoint", "mid.hgck"] + common, cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "--steps", "15", "--resume", "mid.hgck", "--dump", "resumed"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for name in ("heightmap", "sediment"):
+        a = np.fromfile(tmp_path / f"full.{name}.rgba32f", dtype=np.uint32)
+        b = np.fromfile(tmp_path / f"resumed.{name}.rgba32f", dtype=np.uint32)
+        assert np.array_equal(a, b), name
