@@ -208,6 +208,35 @@ def test_steep_terrain_thermal_marks(built):
     ctx.close(); ref.close()
 
 
+@pytest.mark.parametrize("kspeed", [1e-30, 3e8])
+def test_thermal_outflow_generic_division(built, kspeed):
+    """Kspeed so small (or so large) that S = d_t*Kspeed*sharpness*H/2 leaves the range in which the
+    kernel's shared-reciprocal division is proven exact: hg_thermal_outflow must take its generic
+    IEEE-division path (out of line on the device) and still match the oracle bit for bit, denormal
+    outflows included.  One step for the large value (the terrain explodes afterwards)."""
+    n = 128
+    ref = oracle.World(n, seed=SEED); ref.gen_heightmap()
+    H = ref.get(0)
+    rng = np.random.default_rng(9)
+    H[..., 0] += rng.random((n, n), dtype=np.float32) * 6.0
+    H[..., 1] += rng.random((n, n), dtype=np.float32) * 2.0
+    H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]
+    ref.set(0, H)
+    ref.erosion.Kalpha[0], ref.erosion.Kalpha[1] = 0.9, 0.3
+    ref.erosion.Kspeed[0], ref.erosion.Kspeed[1] = kspeed, kspeed
+    ctx = Context(n)
+    ctx.set_erosion(_lib.ErosionData.from_buffer_copy(bytes(ref.erosion)))
+    copy_state(ref, ctx)
+    for _ in range(3 if kspeed < 1 else 1):
+        ctx.dispatch_grid(); ref.dispatch_grid()
+    got = ctx.download(0)
+    assert np.isfinite(got).all()
+    if kspeed > 1:
+        assert not np.array_equal(got[..., :2], H[..., :2])      # something did flow (1e-30 outflows vanish in the sum)
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), f"generic thermal division, Kspeed {kspeed}")
+    ctx.close(); ref.close()
+
+
 def test_exhausted_dirt_layer(built, wet256):
     """Thin dirt + aggressive dissolving: the 'layer went negative -> continue into rock'
     branch of hydro_erosion.glsl:68-77."""
