@@ -31,8 +31,7 @@
 //
 // Exchanges are packed so one LDS/STS moves what a neighbour needs:
 //   XQ  float4 (H.a, rock, dirt, fR)   XL float fL          raw row            N=2
-//   RE  float  rockE                                        after stage A      N=4
-//   DE  float  dirtE (own column only, A -> D)                                 N=8
+//   RD  float2 (rockE, dirtE)                               after stage A      N=4
 //   SS  float2 (S'.rock, S'.dirt)                           after stage A      N=4
 //   OxR float4 (R, RT, RB, -)  OxL float4 (L, LT, LB, -)    thermal outflow    N=2, per layer
 //   R1D float2 (rock1, dirtE)                               after stage D      N=4
@@ -73,22 +72,25 @@ struct HgF2 { float x, y; };
 static_assert(sizeof(HgF4) == 16 && sizeof(HgF2) == 8, "packed ring elements");
 #endif
 
-// Ring offsets in floats inside the CTA's shared block; every ring row has NT+2 elements
-// (one pad element each side so tid-1 / tid+1 of the edge threads stay inside).
+// Ring offsets in BYTES inside the CTA's shared block; every ring row has NT+2 elements (one pad
+// element each side so tid-1 / tid+1 of the edge threads stay inside).  A ring is [rows][E]
+// elements, so the address of (row slot s, element el) is ring + (s*E + el) * sizeof(element):
+// one per-iteration pointer per (element size, slot) serves every ring of that shape, and each
+// access is that pointer plus a compile-time offset.
 template <int NT> struct HgRings {
     static constexpr int E = NT + 2;
-    static constexpr int XQ = 0;                    // float4 [2][E]
-    static constexpr int O0R = XQ + 2 * E * 4;      // float4 [2][E]
-    static constexpr int O0L = O0R + 2 * E * 4;
-    static constexpr int O1R = O0L + 2 * E * 4;
-    static constexpr int O1L = O1R + 2 * E * 4;
-    static constexpr int SS = O1L + 2 * E * 4;      // float2 [4][E]
-    static constexpr int R1D = SS + 4 * E * 2;      // float2 [4][E]
-    static constexpr int G2 = R1D + 4 * E * 2;      // float2 [4][E]
-    static constexpr int XL = G2 + 4 * E * 2;       // float  [2][E]
-    static constexpr int RE = XL + 2 * E;           // float  [4][E]
-    static constexpr int DE = RE + 4 * E;           // float  [8][E]
-    static constexpr int TOTAL = DE + 8 * E;        // 78 * E floats
+    static constexpr int XQ = 0;                     // float4 [2][E]
+    static constexpr int O0R = XQ + 2 * E * 16;      // float4 [2][E]
+    static constexpr int O0L = O0R + 2 * E * 16;
+    static constexpr int O1R = O0L + 2 * E * 16;
+    static constexpr int O1L = O1R + 2 * E * 16;
+    static constexpr int SS = O1L + 2 * E * 16;      // float2 [4][E]
+    static constexpr int RD = SS + 4 * E * 8;        // float2 [4][E]
+    static constexpr int R1D = RD + 4 * E * 8;       // float2 [4][E]
+    static constexpr int G2 = R1D + 4 * E * 8;       // float2 [4][E]
+    static constexpr int XL = G2 + 4 * E * 8;        // float  [2][E]
+    static constexpr int TOTAL_BYTES = XL + 2 * E * 4;
+    static constexpr int TOTAL = TOTAL_BYTES / 4;    // 74 * E floats
 };
 
 struct HgFusedK {
@@ -109,7 +111,7 @@ struct HgCol {
     float f1L, f1R, f1T, f1B, f2L, f2R, f2T, f2B, f0T;
     float s1r, s1d, s2r, s2d;
     float u_d1, v_d1, u_d2, v_d2;                // velocity delayed 1, 2 iterations
-    float e_old;                                 // own rockE of row i-5 (stage D)
+    float e_old, de_old;                         // own (rockE, dirtE) of row i-5 (stage D)
     float so0_d1, so0_d2, T0_d1, T0_d2, T0_d3, B0_d1;
     float nR0_d1, nL0_d1, nRT0_d1, nRT0_d2, nLT0_d1, nLT0_d2;
     float p_old, q_old;                          // own (rock1, dirtE) of row i-9 (stage F)
@@ -134,14 +136,23 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     const HgStepParams& P = K.P;
     const int W = K.W, H = K.H;
     const unsigned pitch = (unsigned)K.pitch;
-    HgF4* const f4 = reinterpret_cast<HgF4*>(sm);
-    HgF2* const f2 = reinterpret_cast<HgF2*>(sm);
     const int e = tid + 1;   // element index inside a ring row
-    // slot of absolute row (i - k) in a ring of n rows
-#define SLOT(k, n) ((i - (k)) & ((n) - 1))
-#define F4(ring, slot, el) f4[(ring) / 4 + (slot) * R::E + (el)]
-#define F2(ring, slot, el) f2[(ring) / 2 + (slot) * R::E + (el)]
-#define F1(ring, slot, el) sm[(ring) + (slot) * R::E + (el)]
+    char* const smc = reinterpret_cast<char*>(sm);
+    // Element index (slot * E + e) of the ring row that holds absolute row i - j: two-row rings
+    // (j = 0, 1) and four-row rings (j = 0..3).  Row i - k lives in slot (i - k) mod n.
+    const int u0 = (i & 1) * R::E + e, u1 = (R::E + 2 * e) - u0;
+    const int v0 = (i & 3) * R::E + e, v1 = ((i - 1) & 3) * R::E + e, v2 = ((i - 2) & 3) * R::E + e, v3 = ((i - 3) & 3) * R::E + e;
+    char* const a16_0 = smc + u0 * 16; char* const a16_1 = smc + u1 * 16;     // float4 rings
+    char* const a4_0 = smc + u0 * 4; char* const a4_1 = smc + u1 * 4;         // float ring (XL)
+    char* const b8_0 = smc + v0 * 8; char* const b8_1 = smc + v1 * 8; char* const b8_2 = smc + v2 * 8; char* const b8_3 = smc + v3 * 8;   // float2 rings
+    // ring: byte offset (HgRings); k: the row is i - k; d: element offset relative to this thread's
+#define A16(k) (((k) & 1) ? a16_1 : a16_0)
+#define A4(k) (((k) & 1) ? a4_1 : a4_0)
+#define B8(k) (((k) & 3) == 0 ? b8_0 : ((k) & 3) == 1 ? b8_1 : ((k) & 3) == 2 ? b8_2 : b8_3)
+#define Q4(ring, k, d) (*reinterpret_cast<HgF4*>(A16(k) + (ring) + (d) * 16))
+#define Q1(ring, k, d) (*reinterpret_cast<float*>(A4(k) + (ring) + (d) * 4))
+#define Q2(ring, k, d) (*reinterpret_cast<HgF2*>(B8(k) + (ring) + (d) * 8))
+#define Q2X(ring, k, d) (reinterpret_cast<const float*>(B8(k) + (ring) + (d) * 8)[0])   /* .x only: a 4-byte load */
 
     if (GROUP != HGF_THERMAL) {
     // ------------------------------------------------------------ L(i)
@@ -160,8 +171,8 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     c.at2 = (xin && (FREE || (i >= 0 && i < H))) ? c.rk2 + c.dt2 + c.w2 : HG_OOB_HEIGHT;
     {
         HgF4 q; q.x = c.at2; q.y = c.rk2; q.z = c.dt2; q.w = c.f2R;
-        F4(R::XQ, SLOT(0, 2), e) = q;
-        F1(R::XL, SLOT(0, 2), e) = c.f2L;
+        Q4(R::XQ, 0, 0) = q;
+        Q1(R::XL, 0, 0) = c.f2L;
     }
 
     // ------------------------------------------------------------ A(i-1)
@@ -170,9 +181,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         const int ya = i - 1;
         if (FREE || (ya >= gy0 - 5 && ya < gy1 + 5)) {
             const bool in = xin && (FREE || (ya >= 0 && ya < H));
-            const HgF4 ql = F4(R::XQ, SLOT(1, 2), e - 1);     // left neighbour: H.a, rock, dirt, fR
-            const HgF4 qr = F4(R::XQ, SLOT(1, 2), e + 1);     // right neighbour: H.a, rock, dirt
-            const float inR = F1(R::XL, SLOT(1, 2), e + 1);   // right neighbour's fL
+            const HgF4 ql = Q4(R::XQ, 1, -1);     // left neighbour: H.a, rock, dirt, fR
+            const HgF4 qr = Q4(R::XQ, 1, 1);      // right neighbour: H.a, rock, dirt
+            const float inR = Q1(R::XL, 1, 1);    // right neighbour's fL
             // FREE rows are strictly inside the map in y: y = 1, H = 4 folds the y-border tests away
             HgFluxOut o = hg_flux_cell(P, x, FREE ? 1 : ya, W, FREE ? 4 : H, c.at1, ql.x, qr.x, c.at2, c.at0,
                                        c.f1L, c.f1R, c.f1T, c.f1B, ql.w, inR, c.f2B, c.f0T, c.w1);
@@ -185,10 +196,10 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 K.dst[5][idx] = o.fT; K.dst[6][idx] = o.fB;
                 K.dst[2][idx] = o.water * P.evap;     // sediment_transport.glsl:75
             }
-            F1(R::RE, SLOT(1, 4), e) = in ? er.rock : HG_OOB_HEIGHT;
-            F1(R::DE, SLOT(1, 8), e) = in ? er.dirt : HG_OOB_HEIGHT;
+            HgF2 rd; rd.x = in ? er.rock : HG_OOB_HEIGHT; rd.y = in ? er.dirt : HG_OOB_HEIGHT;
+            Q2(R::RD, 1, 0) = rd;
             HgF2 s; s.x = in ? er.sr : 0.0f; s.y = in ? er.sd : 0.0f;
-            F2(R::SS, SLOT(1, 4), e) = s;
+            Q2(R::SS, 1, 0) = s;
         }
     }
 
@@ -201,9 +212,10 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             const bool fast = dx >= -1 && dx <= 0 && dy >= -1 && dy <= 0;
             const int cdx = fast ? dx : 0;
             const bool up = fast && dy == -1;          // footprint rows (yb-1, yb) instead of (yb, yb+1)
-            const int r0 = up ? SLOT(4, 4) : SLOT(3, 4), r1 = up ? SLOT(3, 4) : SLOT(2, 4);
-            const HgF2 t00 = F2(R::SS, r0, e + cdx), t10 = F2(R::SS, r0, e + cdx + 1);
-            const HgF2 t01 = F2(R::SS, r1, e + cdx), t11 = F2(R::SS, r1, e + cdx + 1);
+            const char* const r0 = (up ? B8(4) : B8(3)) + R::SS + cdx * 8;
+            const char* const r1 = (up ? B8(3) : B8(2)) + R::SS + cdx * 8;
+            const HgF2 t00 = reinterpret_cast<const HgF2*>(r0)[0], t10 = reinterpret_cast<const HgF2*>(r0)[1];
+            const HgF2 t01 = reinterpret_cast<const HgF2*>(r1)[0], t11 = reinterpret_cast<const HgF2*>(r1)[1];
             float sr = hg_bilerp(t00.x, t10.x, t01.x, t11.x, b.sx, b.sy);
             float sd = hg_bilerp(t00.y, t10.y, t01.y, t11.y, b.sx, b.sy);
             if (owned) {
@@ -227,11 +239,12 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     {
         // rockE window: rows i-4 (y-1), i-3 (y), i-2 (y+1), columns x-1..x+1, straight from the ring
         // (stage A writes row i-1 into the fourth slot meanwhile)
-        const float e00 = F1(R::RE, SLOT(4, 4), e - 1), e01 = F1(R::RE, SLOT(4, 4), e), e02 = F1(R::RE, SLOT(4, 4), e + 1);
-        const float e10 = F1(R::RE, SLOT(3, 4), e - 1), e11 = F1(R::RE, SLOT(3, 4), e), e12 = F1(R::RE, SLOT(3, 4), e + 1);
-        const float e20 = F1(R::RE, SLOT(2, 4), e - 1), e21 = F1(R::RE, SLOT(2, 4), e), e22 = F1(R::RE, SLOT(2, 4), e + 1);
-        const float rockE_d = c.e_old;   // own rockE of row i-5: last iteration's row y-1; D needs it
-        c.e_old = e01;
+        const HgF2 rd01 = Q2(R::RD, 4, 0);
+        const float e00 = Q2X(R::RD, 4, -1), e01 = rd01.x, e02 = Q2X(R::RD, 4, 1);
+        const float e10 = Q2X(R::RD, 3, -1), e11 = Q2X(R::RD, 3, 0), e12 = Q2X(R::RD, 3, 1);
+        const float e20 = Q2X(R::RD, 2, -1), e21 = Q2X(R::RD, 2, 0), e22 = Q2X(R::RD, 2, 1);
+        const float rockE_d = c.e_old, dirtE_d0 = c.de_old;   // own (rockE, dirtE) of row i-5: last iteration's row y-1; D needs them
+        c.e_old = rd01.x; c.de_old = rd01.y;
         const int yc = i - 3;
         float so0 = 0.0f, T0 = 0.0f, B0 = 0.0f;
         if (FREE || (yc >= gy0 - 4 && yc < gy1 + 4)) {
@@ -249,18 +262,18 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             T0 = out[2]; B0 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;    // R, RT, RB
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;    // L, LT, LB
-            F4(R::O0R, SLOT(3, 2), e) = tr;
-            F4(R::O0L, SLOT(3, 2), e) = tl;
+            Q4(R::O0R, 3, 0) = tr;
+            Q4(R::O0L, 3, 0) = tl;
         }
         // D(i-5): neighbours' outflow of row i-4 (written last iteration)
         const int yd = i - 5;
-        const HgF4 nl = F4(R::O0R, SLOT(4, 2), e - 1);     // left neighbour's R, RT, RB
-        const HgF4 nr = F4(R::O0L, SLOT(4, 2), e + 1);     // right neighbour's L, LT, LB
+        const HgF4 nl = Q4(R::O0R, 4, -1);     // left neighbour's R, RT, RB
+        const HgF4 nr = Q4(R::O0L, 4, 1);      // right neighbour's L, LT, LB
         if (FREE || (yd >= gy0 - 3 && yd < gy1 + 3)) {
             const bool in = xin && (FREE || (yd >= 0 && yd < H));
             float delta = hg_thermal_delta(c.so0_d2, c.nR0_d1, c.nL0_d1, c.B0_d1, c.T0_d3, nl.z, nr.z, c.nRT0_d2, c.nLT0_d2);
-            HgF2 w; w.x = in ? rockE_d + delta : HG_OOB_HEIGHT; w.y = F1(R::DE, SLOT(5, 8), e);
-            F2(R::R1D, SLOT(5, 4), e) = w;
+            HgF2 w; w.x = in ? rockE_d + delta : HG_OOB_HEIGHT; w.y = dirtE_d0;
+            Q2(R::R1D, 5, 0) = w;
         }
         c.so0_d2 = c.so0_d1; c.so0_d1 = so0;
         c.T0_d3 = c.T0_d2; c.T0_d2 = c.T0_d1; c.T0_d1 = T0;
@@ -273,9 +286,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     {
         // (rock1, dirtE) window: rows i-8 (y-1), i-7 (y), i-6 (y+1), columns x-1..x+1, from the ring
         // (stage D writes row i-5 into the fourth slot meanwhile)
-        const HgF2 w00 = F2(R::R1D, SLOT(8, 4), e - 1), w01 = F2(R::R1D, SLOT(8, 4), e), w02 = F2(R::R1D, SLOT(8, 4), e + 1);
-        const HgF2 w10 = F2(R::R1D, SLOT(7, 4), e - 1), w11 = F2(R::R1D, SLOT(7, 4), e), w12 = F2(R::R1D, SLOT(7, 4), e + 1);
-        const HgF2 w20 = F2(R::R1D, SLOT(6, 4), e - 1), w21 = F2(R::R1D, SLOT(6, 4), e), w22 = F2(R::R1D, SLOT(6, 4), e + 1);
+        const HgF2 w00 = Q2(R::R1D, 8, -1), w01 = Q2(R::R1D, 8, 0), w02 = Q2(R::R1D, 8, 1);
+        const HgF2 w10 = Q2(R::R1D, 7, -1), w11 = Q2(R::R1D, 7, 0), w12 = Q2(R::R1D, 7, 1);
+        const HgF2 w20 = Q2(R::R1D, 6, -1), w21 = Q2(R::R1D, 6, 0), w22 = Q2(R::R1D, 6, 1);
         const float rock1_d = c.p_old, dirtE_d = c.q_old;     // own (rock1, dirtE) of row i-9: last iteration's row y-1
         c.p_old = w01.x; c.q_old = w01.y;
         const int ye = i - 7;
@@ -295,17 +308,17 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             T1 = out[2]; B1 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;
-            F4(R::O1R, SLOT(7, 2), e) = tr;
-            F4(R::O1L, SLOT(7, 2), e) = tl;
+            Q4(R::O1R, 7, 0) = tr;
+            Q4(R::O1L, 7, 0) = tl;
         }
         const int yf = i - 9;
-        const HgF4 nl = F4(R::O1R, SLOT(8, 2), e - 1);
-        const HgF4 nr = F4(R::O1L, SLOT(8, 2), e + 1);
+        const HgF4 nl = Q4(R::O1R, 8, -1);
+        const HgF4 nr = Q4(R::O1L, 8, 1);
         if (FREE || (yf >= gy0 - 1 && yf < gy1 + 1)) {
             const bool in = xin && (FREE || (yf >= 0 && yf < H));
             float delta = hg_thermal_delta(c.so1_d2, c.nR1_d1, c.nL1_d1, c.B1_d1, c.T1_d3, nl.z, nr.z, c.nRT1_d2, c.nLT1_d2);
             HgF2 w; w.x = rock1_d; w.y = in ? dirtE_d + delta : HG_OOB_HEIGHT;
-            F2(R::G2, SLOT(9, 4), e) = w;
+            Q2(R::G2, 9, 0) = w;
         }
         c.so1_d2 = c.so1_d1; c.so1_d1 = so1;
         c.T1_d3 = c.T1_d2; c.T1_d2 = c.T1_d1; c.T1_d1 = T1;
@@ -324,8 +337,8 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         // own column of (rock1, dirt2): rows i-12 (y-1), i-11 (y), i-10 (y+1); stage F writes row i-9 meanwhile
         const int yg = i - HGF_LAG_G;
         if (FREE || (yg >= gy0 && yg < gy1)) {
-            const HgF2 l = F2(R::G2, SLOT(11, 4), e - 1), r = F2(R::G2, SLOT(11, 4), e + 1);
-            const HgF2 dn = F2(R::G2, SLOT(12, 4), e), own = F2(R::G2, SLOT(11, 4), e), up = F2(R::G2, SLOT(10, 4), e);
+            const HgF2 l = Q2(R::G2, 11, -1), r = Q2(R::G2, 11, 1);
+            const HgF2 dn = Q2(R::G2, 12, 0), own = Q2(R::G2, 11, 0), up = Q2(R::G2, 10, 0);
             float rock = own.x, dirt = own.y;
             float sr_ = rock, sd_ = dirt;
             hg_smooth_cell(P, sr_, sd_, l.x, l.y, r.x, r.y, up.x, up.y, dn.x, dn.y);
@@ -337,10 +350,13 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             }
         }
     }
-#undef SLOT
-#undef F4
-#undef F2
-#undef F1
+#undef A16
+#undef A4
+#undef B8
+#undef Q4
+#undef Q1
+#undef Q2
+#undef Q2X
 }
 
 // The rows of segment [gy0, gy1) for which FREE iterations are legal: every stage row is
