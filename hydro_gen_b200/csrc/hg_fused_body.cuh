@@ -254,11 +254,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             // dropped: it can only turn a -0 difference into +0, and a zero d_h is never marked.
             d_h[0] = e11 - e10; d_h[1] = e11 - e12; d_h[2] = e11 - e21; d_h[3] = e11 - e01;
             d_h[4] = e11 - e20; d_h[5] = e11 - e22; d_h[6] = e11 - e00; d_h[7] = e11 - e02;
-            if (!in) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) d_h[k] = -1.0f;   // an out-of-map cell has no outflow
-            }
-            so0 = hg_thermal_outflow(P, 0, e11, d_h, out);
+            so0 = hg_thermal_outflow(P, 0, e11, d_h, out, in);   // an out-of-map cell has no outflow
             T0 = out[2]; B0 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;    // R, RT, RB
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;    // L, LT, LB
@@ -300,11 +296,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             d_h[2] = (w11.x - w21.x) + (w11.y - w21.y); d_h[3] = (w11.x - w01.x) + (w11.y - w01.y);
             d_h[4] = (w11.x - w20.x) + (w11.y - w20.y); d_h[5] = (w11.x - w22.x) + (w11.y - w22.y);
             d_h[6] = (w11.x - w00.x) + (w11.y - w00.y); d_h[7] = (w11.x - w02.x) + (w11.y - w02.y);
-            if (!in) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) d_h[k] = -1.0f;
-            }
-            so1 = hg_thermal_outflow(P, 1, w11.y, d_h, out);
+            so1 = hg_thermal_outflow(P, 1, w11.y, d_h, out, in);
             T1 = out[2]; B1 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;
             HgF4 tl; tl.x = out[0]; tl.y = out[4]; tl.z = out[6]; tl.w = 0.0f;
