@@ -228,7 +228,15 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
 // instruction issue and latency, not by HBM, and the extra warps are what hides the latency.
 template <int RH> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RH)); }
 template <int RT> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RT)); }
-__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+// The two groups meet at barrier 0 from different loops.  An inline-asm barrier is not a convergent
+// operation for the compiler, which may leave lanes of a warp diverged in front of it (seen with
+// compute-sanitizer synccheck after the guarded stores of stage B): reconverge the warp first, and use
+// the form of the instruction that is defined for unaligned arrival (barrier.sync, not bar.sync =
+// barrier.sync.aligned).
+__device__ __forceinline__ void cta_barrier() {
+    __syncwarp();
+    asm volatile("barrier.sync 0;" ::: "memory");
+}
 
 template <int NT, int MINB, int RH, int RT>
 __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
