@@ -1,4 +1,5 @@
 #!/bin/bash
+# VARIANTS="0 5 8" bash scripts/gpu_variants_env.sh: GPU tests + device-timed bench per HG_FUSED_VARIANT (same box: A/B)
 mkdir -p gpurun_out
 for v in $VARIANTS; do
 HG_FUSED_VARIANT=$v timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -1
