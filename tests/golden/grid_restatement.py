@@ -5,8 +5,10 @@ cell, with Python loops; it shares no code with oracle/hg_oracle.c or with the C
 kernels.  tests/golden/make_golden.py runs it on small seeded cases and commits the
 inputs and outputs as tests/golden/grid_cases.npz; the oracle (CPU tests) and the CUDA
 path (GPU tests) must both reproduce those files bit for bit.  Two restatements written
-separately from the same shader text agreeing to the last bit is the strongest pin
-available: the reference ships no fixtures and its shaders cannot run here.
+separately from the same shader text agreeing to the last bit was the first pin of the
+oracle; since then the reference's own shaders have been compiled for the CPU
+(oracle/refshader/) and reproduce the files written by this module bit for bit
+(tests/test_refshaders.py).
 
 Every numpy float32 scalar operation is one correctly rounded IEEE operation, so the
 operand order below IS the arithmetic.  Images are float32 arrays [y][x][4].

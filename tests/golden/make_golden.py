@@ -13,8 +13,10 @@ oracle_runs.npz  seed-fixed oracle dumps (64x64: heightmap init; 40 main-loop it
                  rain every 8 steps; 48x80 non-square) so the GPU tests can also run against
                  committed files, and so a change of the oracle itself is caught.
 
-The reference has no fixtures of its own and cannot run here; these
-files are what pins the oracle.  Neither generator touches /root/reference at run time.
+The reference has no fixtures of its own.  These files were the first pin of the
+oracle; tests/golden/make_ref_golden.py adds outputs of the reference's own shaders compiled for
+the CPU, which also reproduce grid_cases.npz bit for bit.  Neither generator here touches
+/root/reference at run time.
 """
 import os
 import sys

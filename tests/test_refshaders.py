@@ -1,0 +1,126 @@
+"""The oracle restatement (oracle/hg_oracle.c) against the REFERENCE'S OWN shaders, compiled for the CPU
+from /root/reference/glsl/*.glsl by oracle/refshader/build_ref.py (oracle/_ref/libhg_refshaders.so; the
+built library travels to the GPU box, the sources are only needed to build it).
+
+Every dispatch of Erosion::dispatch_grid (src/erosion.cpp:158-200) and Erosion::dispatch_grid_rain is run
+by both on the same inputs; all six textures must agree BIT FOR BIT after each dispatch, on a wet state
+in which every branch is live, and after whole multi-step runs.  What this pins: expression structure and
+association order, constants, branch structure, neighbour indexing, border rules, texture bindings and
+swap order — everything the restatement could have got wrong.  (Built-ins GLSL leaves open — atan, the
+formulas of min/max/mix/... — are the documented ones of include/hg_defined_math.h on both sides.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import refshaders
+from tests.util import DT_TIME, SEED, assert_bit_equal, wet_world
+
+pytestmark = pytest.mark.skipif(not refshaders.available(), reason="oracle/_ref/libhg_refshaders.so not built (needs /root/reference)")
+
+FIELDS = ("heightmap", "flux", "velocity", "sediment", "thermal_c", "thermal_d")
+
+
+def _ref_from(orc):
+    """RefWorld with the oracle's current read textures and settings."""
+    e = oracle.ErosionData.from_buffer_copy(bytes(orc.erosion))
+    r = oracle.RainData.from_buffer_copy(bytes(orc.rain))
+    m = oracle.MapSettingsData.from_buffer_copy(bytes(orc.map))
+    ref = refshaders.RefWorld(orc.W, e, r, m)
+    for k, f in enumerate(FIELDS):
+        getattr(ref, f).read[...] = orc.get(k)
+    return ref
+
+
+def _compare(ref, orc, what, fields=FIELDS):
+    for k, f in enumerate(FIELDS):
+        if f in fields:
+            assert_bit_equal(orc.get(k), getattr(ref, f).read, f"{what}: {f}")
+
+
+@pytest.fixture(scope="module")
+def wet():
+    w = wet_world(96, 200, period=8)
+    yield w
+    w.close()
+
+
+def test_each_dispatch_matches_the_reference_shaders(wet):
+    orc = wet
+    ref = _ref_from(orc)
+    for which, name in enumerate(refshaders.RefWorld.PASSES):
+        getattr(ref, name)()
+        orc.run_pass(which)
+        _compare(ref, orc, name)
+    # the wet state exercises the hydraulics; check it is not a trivial comparison
+    assert orc.get(0)[..., 2].max() > 0 and np.abs(orc.get(1)).max() > 0 and orc.get(3)[..., :2].max() > 0
+
+
+def test_rain_matches_the_reference_shader(wet):
+    orc = wet
+    ref = _ref_from(orc)
+    t = 201 * DT_TIME
+    ref.dispatch_grid_rain(t)
+    orc.dispatch_grid_rain(t)
+    _compare(ref, orc, "rain", ("heightmap",))
+
+
+@pytest.mark.parametrize("variant", ["default", "steep_fast", "thin_dirt"])
+def test_multi_step_runs_match_the_reference_shaders(variant):
+    """main-loop iterations (src/main.cpp:310-321) from the generated terrain: rain when due, then the 8 dispatches"""
+    n = 64
+    orc = oracle.World(n, seed=SEED)
+    orc.gen_heightmap()
+    orc.rain.period = 4
+    if variant == "steep_fast":
+        orc.erosion.Kalpha[0], orc.erosion.Kalpha[1] = 0.5, 0.2
+        orc.erosion.d_t = 0.02
+        orc.rain.amount = 0.5
+    if variant == "thin_dirt":
+        H = orc.get(0); H[..., 1] = 1e-4; H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]; orc.set(0, H)
+        orc.erosion.Ks[1] = 50.0; orc.erosion.Kc = 5.0
+        orc.rain.amount = 0.3
+    ref = _ref_from(orc)
+    thermal = 0.0
+    for s in range(1, 25):
+        t = float(np.float32(s) * np.float32(DT_TIME))
+        ref.step(s, t)
+        orc.step(t)
+        _compare(ref, orc, f"{variant} step {s}")
+        thermal = max(thermal, float(np.abs(orc.get(4)).max()), float(np.abs(orc.get(5)).max()))
+    assert orc.get(0)[..., 2].max() > 0
+    if variant == "steep_fast":
+        assert thermal > 0          # thermal outflow (both neighbour classes) was live
+    orc.close()
+
+
+# ---- the committed golden vectors ARE the reference shaders' outputs ------------------------------------
+def _ref_for_case(cases, name):
+    from tests.test_golden import apply_params
+    Hm = cases[f"{name}/in/H"]
+    assert Hm.shape[0] == Hm.shape[1]
+    w = oracle.World(8)                              # only for the default settings blocks
+    e = apply_params(oracle.ErosionData.from_buffer_copy(bytes(w.erosion)), cases[f"{name}/params"])
+    ref = refshaders.RefWorld(Hm.shape[1], e, oracle.RainData.from_buffer_copy(bytes(w.rain)), oracle.MapSettingsData.from_buffer_copy(bytes(w.map)))
+    w.close()
+    return ref
+
+
+@pytest.mark.parametrize("name", ["default_wet", "steep_thermal"])       # the square cases (RefWorld textures are n x n)
+def test_committed_golden_vectors_are_the_reference_shaders_outputs(name):
+    """tests/golden/grid_cases.npz was written by an independent numpy restatement before the reference
+    shaders could be run here; the shaders reproduce every image in it bit for bit."""
+    import os
+    from tests.test_golden import PASS_CHECKS
+    cases = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grid_cases.npz"))
+    ref = _ref_for_case(cases, name)
+    for k, f in (("H", "heightmap"), ("F", "flux"), ("V", "velocity"), ("S", "sediment")):
+        getattr(ref, f).read[...] = cases[f"{name}/in/{k}"]
+    for (stage, _, fields), method in zip(PASS_CHECKS, refshaders.RefWorld.PASSES):
+        getattr(ref, method)()
+        for j, f in enumerate(fields):
+            assert_bit_equal(getattr(ref, f).read, cases[f"{name}/step1/{stage}/{j}"], f"{name} after {stage}: {f}")
+    ref.dispatch_grid(); ref.dispatch_grid()
+    for k, f in (("H", "heightmap"), ("F", "flux"), ("V", "velocity"), ("S", "sediment")):
+        assert_bit_equal(getattr(ref, f).read, cases[f"{name}/step3/out/{k}"], f"{name} step 3: {f}")
