@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this package; the product
-(hydro_gen_b200) never does.  The grid path is pinned against the reference's own
+(hydro_gen_b200) never does.  It is pinned against the reference's own
 shaders compiled for the CPU (oracle/refshader/, oracle/refshaders.py; see the
 hg_oracle.c header and DESIGN.md §Oracle).
 """

@@ -7,15 +7,14 @@
  * the product library; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may use it.
  *
- * PINNED AGAINST THE REFERENCE'S OWN SHADERS (grid path: the six step shaders
- * and rain): the reference ships no tests or fixtures and there
- * is no GL here, but its compute shaders compile for the CPU through a C++ shim
- * of the GLSL vocabulary (oracle/refshader/, output oracle/_ref/).  This
- * restatement reproduces them bit for bit after every dispatch and over
- * multi-step runs (tests/test_refshaders.py), and so do the committed fixtures
- * (tests/golden/).  Still anchored on the shader text alone: heightmap.glsl and
- * the droplet shaders (pinned only by the independent numpy restatement /
- * hand-derived cases).  Every function cites the file:line it follows.
+ * PINNED AGAINST THE REFERENCE'S OWN SHADERS: the reference ships no tests or
+ * fixtures and there is no GL here, but its ten compute shaders
+ * (six step shaders, rain, heightmap, particle, particle_erosion) compile for
+ * the CPU through a C++ shim of the GLSL vocabulary (oracle/refshader/, output
+ * oracle/_ref/).  This restatement reproduces them bit for bit after every
+ * dispatch, over multi-step grid and droplet runs and for the generated terrain
+ * (tests/test_refshaders.py), and so do the committed fixtures (tests/golden/).
+ * Every function cites the file:line it follows.
  *
  * Arithmetic rules: every GLSL expression is written with the same operand
  * order and association; build with -ffp-contract=off so no FMA is formed.

@@ -1,5 +1,5 @@
 /* hg_oracle.h — CPU parity oracle for the erosion step.  TEST INFRASTRUCTURE:
- * see the header of hg_oracle.c.  Grid path pinned against the reference's own shaders compiled for the CPU (oracle/refshader/). */
+ * see the header of hg_oracle.c.  Pinned against the reference's own shaders compiled for the CPU (oracle/refshader/). */
 #ifndef HG_ORACLE_H
 #define HG_ORACLE_H
 

@@ -39,6 +39,8 @@ SHADERS = {
     "hydro_flux": [], "hydro_erosion": [], "sediment_transport": [], "thermal_erosion": [],
     "thermal_transport": [], "smoothing": [],
     "rain": ["MAX_FBM_ITERATIONS", "gln_tFBMOpts", "gln_rand3", "gln_simplex", "gln_sfbm"],
+    "particle": [], "particle_erosion": [],
+    "heightmap": ["MAX_FBM_ITERATIONS", "gln_tFBMOpts", "gln_rand3", "gln_simplex", "gln_sfbm", "hash", "noised", "perlfbm", "erosion_perlfbm"],
 }
 
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(f?)(?![\w.])")
@@ -83,7 +85,7 @@ def slice_items(src, names):
 
 def translate(shader):
     src = strip_comments(read(shader))
-    binds, blocks, plain = [], [], []
+    binds, blocks, plain, buffers = [], [], [], []
 
     def include(m):
         name = m.group(1)
@@ -97,12 +99,18 @@ def translate(shader):
     def image(m):
         binds.append(m.group(2))
         return f"{m.group(1)} {m.group(2)};"
-    src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+(?:readonly\s+|writeonly\s+)?(sampler2D|image2D)\s+(\w+)\s*;", image, src)
+    src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+(?:(?:readonly|writeonly|volatile|coherent|restrict)\s+)*(sampler2D|image2D|uimage2D)\s+(\w+)\s*;", image, src)
 
     def block(m):
         blocks.append((m.group(1), m.group(2)))
         return f"{m.group(1)} {m.group(2)};"
     src = re.sub(r"layout\s*\(\s*std140[^)]*\)\s*uniform\s+\w+\s*\{\s*(\w+)\s+(\w+)\s*;\s*\}\s*;", block, src)
+
+    # the droplet SSBO (heightmap.glsl only clears it under #if defined(PARTICLE_COUNT), which the grid build does not define)
+    def ssbo(m):
+        buffers.append((m.group(1), m.group(2), m.group(3)))
+        return f"{m.group(2)}* {m.group(3)} = nullptr;"
+    src = re.sub(r"layout\s*\(\s*std430[^)]*\)\s*buffer\s+(\w+)\s*\{\s*(\w+)\s+(\w+)\s*\[\s*\]\s*;\s*\}\s*;", ssbo, src)
 
     def uniform(m):
         plain.append((m.group(1), m.group(2)))
@@ -112,7 +120,7 @@ def translate(shader):
         raise SystemExit(f"{shader}: a declaration the translator does not know:\n" + "\n".join(l for l in src.split("\n") if re.search(r"layout|uniform|buffer", l)))
     src = FLOAT_LIT.sub(lambda m: m.group(1) + "f", src)
     src = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", src)
-    return src, binds, blocks, plain
+    return src, binds, blocks, plain, buffers
 
 
 def generate():
@@ -120,17 +128,26 @@ def generate():
              "namespace glsl { thread_local U3 gl_GlobalInvocationID, gl_NumWorkGroups, gl_WorkGroupSize; }\n"]
     table = []
     for k, shader in enumerate(SHADERS):
-        src, binds, blocks, plain = translate(shader)
+        src, binds, blocks, plain, buffers = translate(shader)
         # bindings.glsl has an include guard: lift it so that every namespace gets its own copy
         src = src.replace("HYDR_GL_BINDINGS_HPP", f"HYDR_GL_BINDINGS_{k}")
-        parts.append(f"namespace glsl {{ namespace ref_{shader} {{\n{src}\n")
+        parts.append(f"namespace glsl {{ namespace ref_{shader} {{\n#define bool gbool\n{src}\n#undef bool\n")
         parts.append("static int bind(const char* n, float* p, int w, int h) {\n")
         for b in binds:
-            parts.append(f'    if (!strcmp(n, "{b}")) {{ {b}.p = p; {b}.w = w; {b}.h = h; return 0; }}\n')
+            parts.append(f'    if (!strcmp(n, "{b}")) {{ {b}.p = (decltype({b}.p))p; {b}.w = w; {b}.h = h; return 0; }}\n')
+        for blk, t, n in buffers:
+            parts.append(f'    if (!strcmp(n, "{blk}")) {{ {n} = ({t}*)p; return 0; }}\n')
         parts.append("    return -1;\n}\nstatic int set_uniform(const char* n, const void* p, int bytes) {\n")
         for t, n in blocks + plain:
             parts.append(f'    if (!strcmp(n, "{n}")) {{ if (bytes != (int)sizeof({n})) return -2; memcpy(&{n}, p, sizeof({n})); return 0; }}\n')
         parts.append("    return -1;\n}\n")
+        parts.append("static int run1d(int count) {\n"
+                     "    gl_WorkGroupSize.x = WRKGRP_SIZE_X * WRKGRP_SIZE_Y; gl_WorkGroupSize.y = 1; gl_WorkGroupSize.z = 1;\n"
+                     "    gl_NumWorkGroups.x = count / (WRKGRP_SIZE_X * WRKGRP_SIZE_Y); gl_NumWorkGroups.y = 1; gl_NumWorkGroups.z = 1;\n"
+                     "    for (int id = 0; id < count; id++) {\n"
+                     "        gl_GlobalInvocationID.x = id; gl_GlobalInvocationID.y = 0; gl_GlobalInvocationID.z = 0;\n"
+                     "        gl_GlobalInvocationID.xy = uvec2(id, 0);\n"
+                     "        shader_main();\n    }\n    return 0;\n}\n")
         parts.append("static int run(int W, int H) {\n"
                      "    gl_WorkGroupSize.x = WRKGRP_SIZE_X; gl_WorkGroupSize.y = WRKGRP_SIZE_Y; gl_WorkGroupSize.z = 1;\n"
                      "    gl_NumWorkGroups.x = W / WRKGRP_SIZE_X; gl_NumWorkGroups.y = H / WRKGRP_SIZE_Y; gl_NumWorkGroups.z = 1;\n"
@@ -138,13 +155,14 @@ def generate():
                      "        gl_GlobalInvocationID.x = x; gl_GlobalInvocationID.y = y; gl_GlobalInvocationID.z = 0;\n"
                      "        gl_GlobalInvocationID.xy = uvec2(x, y);\n"
                      "        shader_main();\n    }\n    return 0;\n}\n")
-        parts.append("static_assert(sizeof(Erosion_data) == 96 && sizeof(Rain_data) == 20 && sizeof(Map_settings_data) == 96, \"std140 images of the settings blocks\");\n")
+        parts.append("static_assert(sizeof(Erosion_data) == 96 && sizeof(Rain_data) == 20 && sizeof(Map_settings_data) == 96 && sizeof(Particle) == 48, \"std140 / std430 images of the blocks\");\n")
         parts.append("} }\n")
         table.append(shader)
     parts.append('extern "C" {\n')
     for fn, sig, call in (("ref_bind", "const char* s, const char* n, float* p, int w, int h", "bind(n, p, w, h)"),
                           ("ref_set_uniform", "const char* s, const char* n, const void* p, int bytes", "set_uniform(n, p, bytes)"),
-                          ("ref_run", "const char* s, int W, int H", "run(W, H)")):
+                          ("ref_run", "const char* s, int W, int H", "run(W, H)"),
+                          ("ref_run1d", "const char* s, int count", "run1d(count)")):
         parts.append(f"int {fn}({sig}) {{\n")
         for shader in table:
             parts.append(f'    if (!strcmp(s, "{shader}")) return glsl::ref_{shader}::{call};\n')

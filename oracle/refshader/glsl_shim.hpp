@@ -21,6 +21,7 @@ namespace glsl {
 
 typedef unsigned int uint;
 struct vec2; struct vec3; struct vec4; struct ivec2; struct uvec2; struct uvec3;
+struct IXY { int d[2]; operator ivec2() const; };      // ivec2 .xy
 
 // ---- swizzles: views into the parent's storage (N = parent size) ----
 template <int N, int A, int B> struct Sw2 {
@@ -53,7 +54,7 @@ struct alignas(8) vec2 {
     vec2(float a, float b) : x(a), y(b) {}
     vec2(const vec2& o) : x(o.x), y(o.y) {}
     vec2& operator=(const vec2& o) { x = o.x; y = o.y; return *this; }
-    vec2(const ivec2& v); vec2(const uvec2& v);
+    vec2(const ivec2& v); vec2(const uvec2& v); vec2(const struct IXY& v);
     float& operator[](int i) { return d[i]; }
     float operator[](int i) const { return d[i]; }
     vec2& operator+=(const vec2& o) { x += o.x; y += o.y; return *this; }
@@ -72,6 +73,7 @@ struct vec3 {
     vec3(float a) : x(a), y(a), z(a) {}
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
     vec3(const vec2& a, float c) : x(a.x), y(a.y), z(c) {}
+    vec3(float a, const vec2& b) : x(a), y(b.x), z(b.y) {}
     vec3(const vec3& o) : x(o.x), y(o.y), z(o.z) {}
     vec3& operator=(const vec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
     float& operator[](int i) { return d[i]; }
@@ -104,14 +106,17 @@ struct vec4 {
     vec4& operator*=(float s) { x *= s; y *= s; z *= s; w *= s; return *this; }
 };
 struct alignas(8) ivec2 {
-    int x, y;
+    union { struct { int x, y; }; IXY xy; };
     ivec2() : x(0), y(0) {}
     ivec2(int a) : x(a), y(a) {}
     ivec2(int a, int b) : x(a), y(b) {}
+    ivec2(const ivec2& o) : x(o.x), y(o.y) {}
+    ivec2& operator=(const ivec2& o) { x = o.x; y = o.y; return *this; }
     explicit ivec2(const vec2& v) : x((int)v.x), y((int)v.y) {}     // float -> int conversion truncates (GLSL 4.60 §5.4.1)
     explicit ivec2(const uvec2& v);
     template <int N, int A, int B> explicit ivec2(const Sw2<N, A, B>& s) : x((int)s.d[A]), y((int)s.d[B]) {}
 };
+inline IXY::operator ivec2() const { return ivec2(d[0], d[1]); }
 struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} };
 struct uvec3 {
     union { struct { uint x, y, z; }; struct { uint d[3]; }; };
@@ -121,6 +126,7 @@ struct uvec3 {
 };
 inline ivec2::ivec2(const uvec2& v) : x((int)v.x), y((int)v.y) {}
 inline vec2::vec2(const ivec2& v) : x((float)v.x), y((float)v.y) {}
+inline vec2::vec2(const IXY& v) : x((float)v.d[0]), y((float)v.d[1]) {}
 inline vec2::vec2(const uvec2& v) : x((float)v.x), y((float)v.y) {}
 
 template <int N, int A, int B> Sw2<N, A, B>::operator vec2() const { return vec2(d[A], d[B]); }
@@ -132,9 +138,13 @@ template <int N, int A, int B, int C> Sw3<N, A, B, C>::operator vec3() const { r
 template <int N, int A, int B, int C> Sw3<N, A, B, C>& Sw3<N, A, B, C>::operator=(const vec3& v) { d[A] = v.x; d[B] = v.y; d[C] = v.z; return *this; }
 template <int N, int A, int B, int C, int D> Sw4<N, A, B, C, D>::operator vec4() const { return vec4(d[A], d[B], d[C], d[D]); }
 
-inline ivec2 operator+(const ivec2& a, const ivec2& b) { return ivec2(a.x + b.x, a.y + b.y); }
-inline ivec2 operator-(const ivec2& a, const ivec2& b) { return ivec2(a.x - b.x, a.y - b.y); }
-inline ivec2 operator*(const ivec2& a, const ivec2& b) { return ivec2(a.x * b.x, a.y * b.y); }
+// GLSL int arithmetic wraps modulo 2^32 (GLSL 4.60 §4.1.3): done in uint32 here, signed overflow is undefined in C++
+#define GLSL_IOP(OP)                                                                                                   \
+    inline ivec2 operator OP(const ivec2& a, const ivec2& b) { return ivec2((int)((uint)a.x OP (uint)b.x), (int)((uint)a.y OP (uint)b.y)); } \
+    inline ivec2 operator OP(const ivec2& a, int b) { return ivec2((int)((uint)a.x OP (uint)b), (int)((uint)a.y OP (uint)b)); }               \
+    inline ivec2 operator OP(int a, const ivec2& b) { return ivec2((int)((uint)a OP (uint)b.x), (int)((uint)a OP (uint)b.y)); }
+GLSL_IOP(+) GLSL_IOP(-) GLSL_IOP(*) GLSL_IOP(^) GLSL_IOP(&)
+inline ivec2 operator<<(const ivec2& a, int s) { return ivec2((int)((uint)a.x << s), (int)((uint)a.y << s)); }
 inline bool operator==(const ivec2& a, const ivec2& b) { return a.x == b.x && a.y == b.y; }
 
 // component-wise arithmetic; scalars broadcast.  S is float, or int/uint/double literals converted to float.
@@ -170,7 +180,9 @@ inline float length(float x) { return fabsf(x); }                // sqrt(x*x) fo
 inline float atan(float x) { return hg_atanf(x); }
 inline float exp(float x) { return hg_expf(x); }
 inline float sin(float x) { return hg_sinf(x); }
-inline float pow(float x, float y) { return y == 1.0f ? x : powf(x, y); }
+// pow is implementation-defined in GLSL; the exponents the shaders use are literal 1, 2 and 3: repeated products
+inline float pow(float x, float y) { return y == 1.0f ? x : y == 2.0f ? x * x : y == 3.0f ? x * x * x : powf(x, y); }
+template <class B> inline float pow(float x, B y) { return pow(x, (float)y); }
 inline float smoothstep(float e0, float e1, float x) { return hg_smoothstep(e0, e1, x); }
 inline float step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
 // vectors
@@ -217,6 +229,35 @@ inline void imageStore(const Image& im, const ivec2& q, const vec4& v) {
     float* t = im.p + ((size_t)q.y * im.w + q.x) * 4;
     t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
 }
+// r32ui image (the droplet lock map) and its atomics; invocations run one after the other here, so a lock is
+// always free when it is tried and the spin loop of particle_erosion.glsl:89-99 takes it at once
+struct uimage2D {
+    uint* p; int w, h;
+    uimage2D() : p(nullptr), w(0), h(0) {}
+    uint* at(const ivec2& q) const { return (p && q.x >= 0 && q.y >= 0 && q.x < w && q.y < h) ? p + (size_t)q.y * w + q.x : nullptr; }
+};
+inline uint imageAtomicCompSwap(const uimage2D& im, const ivec2& q, uint compare, uint data) {
+    uint* t = im.at(q);
+    if (!t) return 0u;                 // out of bounds: the load returns 0 and nothing is stored
+    uint old = *t;
+    if (old == compare) *t = data;
+    return old;
+}
+inline uint imageAtomicExchange(const uimage2D& im, const ivec2& q, uint data) {
+    uint* t = im.at(q);
+    if (!t) return 0u;
+    uint old = *t; *t = data; return old;
+}
+inline void memoryBarrierImage() {}
+inline void barrier() {}
+inline vec2 normalize(const vec2& a) { float inv = 1.0f / length(a); return vec2(a.x * inv, a.y * inv); }
+// GLSL bool occupies 4 bytes in a buffer block (std430) and as a uniform
+struct gbool {
+    uint v;
+    gbool() : v(0) {}
+    gbool(bool b) : v(b ? 1u : 0u) {}
+    operator bool() const { return v != 0; }
+};
 inline ivec2 imageSize(const Image& im) { return ivec2(im.w, im.h); }
 inline ivec2 textureSize(const Image& im, int) { return ivec2(im.w, im.h); }
 

@@ -36,6 +36,7 @@ def lib():
         L.ref_bind.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         L.ref_set_uniform.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int]
         L.ref_run.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        L.ref_run1d.argtypes = [C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -63,10 +64,14 @@ class RefWorld:
     """State::World::Textures (src/state.cpp:3-44) + the settings, stepped by the reference's shaders."""
     FIELDS = ("heightmap", "flux", "velocity", "sediment", "thermal_c", "thermal_d")
 
-    def __init__(self, n, erosion, rain, map_settings):
+    def __init__(self, n, erosion, rain, map_settings, particle_count=0):
         self.n, self.L = n, lib()
         for f in self.FIELDS:
             setattr(self, f, TexPair(n))
+        # droplet mode (src/state.cpp:23-33): r32ui lock map and the Particle SSBO, zero-initialised
+        self.particle_count = particle_count
+        self.lockmap = np.zeros((n, n), np.uint32)
+        self.particle_buffer = np.zeros(max(particle_count, 1) * 48, np.uint8)
         self.erosion, self.rain, self.map = erosion, rain, map_settings     # ctypes images of the std140 blocks
         self.time = 0.0
 
@@ -84,6 +89,13 @@ class RefWorld:
     def _run(self, shader):
         if self.L.ref_run(shader.encode(), self.n, self.n) != 0:
             raise RuntimeError(shader)
+
+    def gen_heightmap(self):                                 # src/state.cpp:116-147 (State::World::gen_heightmap)
+        self._uniform("heightmap", "cfg", self.map)
+        self._bind("heightmap", dest_heightmap=self.heightmap.write, dest_vel=self.velocity.write,
+                   dest_flux=self.flux.write, dest_sediment=self.sediment.write)
+        self._run("heightmap")
+        self.heightmap.swap(); self.velocity.swap(); self.flux.swap(); self.sediment.swap()
 
     def dispatch_grid_rain(self, time):                      # src/erosion.cpp:76-89
         self._uniform("rain", "time", C.c_float(time))
@@ -132,6 +144,42 @@ class RefWorld:
         self._bind("smoothing", heightmap=self.heightmap.read, out_heightmap=self.heightmap.write)
         self._run("smoothing")
         self.heightmap.swap()
+
+    def _run1d(self, shader, count):
+        count = count // 64 * 64          # run_particles dispatches particle_count / (8 * 8) work groups of 64 (src/erosion.cpp:124-130)
+        if self.L.ref_run1d(shader.encode(), count) != 0:
+            raise RuntimeError(shader)
+
+    def _bind_buffer(self, shader, block, arr):
+        if self.L.ref_bind(shader.encode(), block.encode(), arr.ctypes.data, 0, 0) != 0:
+            raise RuntimeError(f"{shader} has no buffer block {block}")
+
+    def particle_move(self, time, should_rain):              # src/erosion.cpp:132-138
+        self._uniform("particle", "time", C.c_float(time))
+        self._uniform("particle", "should_rain", C.c_uint32(1 if should_rain else 0))
+        self._uniform("particle", "set", self.erosion)
+        self._uniform("particle", "map_set", self.map)
+        self._bind("particle", heightmap=self.heightmap.read, momentmap=self.velocity.read)
+        self._bind_buffer("particle", "ParticleBuffer", self.particle_buffer)
+        self._run1d("particle", self.particle_count)
+
+    def particle_erode(self):                                # src/erosion.cpp:140-144
+        self._uniform("particle_erosion", "set", self.erosion)
+        if self.L.ref_bind(b"particle_erosion", b"lockmap", self.lockmap.ctypes.data, self.n, self.n) != 0:
+            raise RuntimeError("lockmap")
+        self._bind("particle_erosion", heightmap=self.heightmap.read, momentmap=self.velocity.read)
+        self._bind_buffer("particle_erosion", "ParticleBuffer", self.particle_buffer)
+        self._run1d("particle_erosion", self.particle_count)
+
+    def dispatch_particle(self, time, should_rain=True):     # src/erosion.cpp:132-156
+        self.particle_move(time, should_rain)
+        self.particle_erode()
+        self.run_thermal_erosion()
+        self._uniform("smoothing", "set", self.erosion)
+        self._bind("smoothing", heightmap=self.heightmap.read, momentmap=self.velocity.read,
+                   out_heightmap=self.heightmap.write, out_momentmap=self.velocity.write)
+        self._run("smoothing")
+        self.heightmap.swap(); self.velocity.swap()
 
     PASSES = ("pass_flux", "pass_erosion", "pass_sediment", "run_thermal_erosion", "pass_smooth")
 

@@ -5,7 +5,8 @@
 
 The reference's own compute shaders, compiled for the CPU (oracle/refshader/build_ref.py) and driven like
 src/main.cpp:310-321 / src/erosion.cpp:76-200 (oracle/refshaders.py), advance seeded 48x48 states; the inputs
-and the heightmap / flux / sediment images after 1, 8 and 16 main-loop iterations are stored.  The oracle
+and the heightmap / flux / sediment images after 1, 8 and 16 main-loop iterations are stored, plus the terrain
+heightmap.glsl generates at 64x64 and a 5-step sparse droplet run (heightmap, momentum map, droplet buffer).  The oracle
 (CPU test) and the CUDA path (GPU test, where /root/reference does not exist) must reproduce them bit for bit
 (tests/test_refshaders.py).  Initial terrains come from the oracle's heightmap generator: they are inputs here,
 not something under test."""
@@ -67,6 +68,48 @@ def main():
                 for k, f in (("H", "heightmap"), ("F", "flux"), ("S", "sediment")):
                     out[f"{name}/step{s}/{k}"] = getattr(ref, f).read.copy()
         w.close()
+    # heightmap.glsl: the generated terrain itself (default map settings)
+    w = oracle.World(64, seed=SEED)
+    ref = refshaders.RefWorld(64, oracle.ErosionData.from_buffer_copy(bytes(w.erosion)), oracle.RainData.from_buffer_copy(bytes(w.rain)),
+                              oracle.MapSettingsData.from_buffer_copy(bytes(w.map)))
+    ref.gen_heightmap()
+    out["init64/H"] = ref.heightmap.read.copy()
+    w.close()
+    # droplet mode, sparse: 64 droplets (one work group) on 128^2, with a spawn time for which no two droplets ever
+    # touch the same texel in these steps, so the result does not depend on lock order and the GPU path (atomics,
+    # any order) must reproduce it exactly.  The time offset is searched; collisions are detected from the quads.
+    n, count = 128, 64
+    part_dt = np.dtype([("sc", "<f4"), ("iters", "<i4"), ("position", "<f4", 2), ("velocity", "<f4", 2), ("volume", "<f4"),
+                        ("_p0", "<u4"), ("sediment", "<f4", 2), ("to_kill", "<u4"), ("_p1", "<u4")])
+    for t0 in range(0, 200):
+        w = oracle.World(n, particle_count=count, erosion_type=1, seed=SEED)
+        w.gen_heightmap()
+        w.map.hmap_dims[0], w.map.hmap_dims[1] = n, n
+        ref = refshaders.RefWorld(n, oracle.ErosionData.from_buffer_copy(bytes(w.erosion)), oracle.RainData.from_buffer_copy(bytes(w.rain)),
+                                  oracle.MapSettingsData.from_buffer_copy(bytes(w.map)), particle_count=count)
+        H0 = w.get(0)
+        ref.heightmap.read[...] = H0
+        w.close()
+        clean = True
+        for s in range(1, 6):
+            ref.dispatch_particle(time_of(t0 + s), True)
+            p = np.frombuffer(ref.particle_buffer[:count * 48].tobytes(), dtype=part_dt)
+            live = p["iters"] > 0
+            base = np.floor(p["position"][live]).astype(np.int64)
+            quads = np.concatenate([base + np.array(o) for o in ((0, 0), (1, 0), (1, 1), (0, 1))])
+            if len({(int(a), int(b)) for a, b in quads}) != len(quads):
+                clean = False
+                break
+        if clean:
+            break
+    else:
+        raise SystemExit("no collision-free droplet case found")
+    out["drops/t0"] = np.int32(t0)
+    out["drops/in/H"] = H0
+    out["drops/step5/H"] = ref.heightmap.read.copy()
+    out["drops/step5/M"] = ref.velocity.read.copy()
+    out["drops/step5/particles"] = ref.particle_buffer[:count * 48].copy()
+    print("droplet case: time offset", t0)
     path = os.path.join(HERE, "refshader_runs.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

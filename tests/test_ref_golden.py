@@ -66,3 +66,41 @@ def test_cuda_reproduces_reference_shader_runs(built, runs, name):
             for k, fid in (("H", 0), ("F", 1), ("S", 3)):
                 assert_bit_equal(ctx.download(fid), runs[f"{name}/step{s}/{k}"], f"{name} step {s}: {k}")
     ctx.close()
+
+
+def test_oracle_reproduces_reference_heightmap_and_droplets(runs):
+    w = oracle.World(64, seed=1234.5)
+    w.gen_heightmap()
+    assert_bit_equal(w.get(0), runs["init64/H"], "heightmap.glsl at 64x64")
+    w.close()
+    n, count = 128, 64
+    w = oracle.World(n, particle_count=count, erosion_type=1, seed=1234.5)
+    w.set(0, runs["drops/in/H"])
+    w.map.hmap_dims[0], w.map.hmap_dims[1] = n, n
+    for s in range(1, 6):
+        w.dispatch_particle(_time(int(runs["drops/t0"]) + s), True)
+    assert w.particles().tobytes() == runs["drops/step5/particles"].tobytes()
+    assert_bit_equal(w.get(0), runs["drops/step5/H"], "droplets: heightmap")
+    assert_bit_equal(w.get(2), runs["drops/step5/M"], "droplets: momentum map")
+    w.close()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_heightmap_and_droplets(built, runs):
+    from hydro_gen_b200 import Context, _lib
+    ctx = Context(64)
+    m = ctx.get_map(); m.seed = 1234.5; ctx.set_map(m)
+    ctx.gen_heightmap()
+    assert_bit_equal(ctx.download(0), runs["init64/H"], "heightmap.glsl at 64x64")
+    ctx.close()
+    n, count = 128, 64
+    ctx = Context(n, particle_count=count, erosion_type=_lib.HG_PARTICLES)
+    m = ctx.get_map(); m.seed = 1234.5; m.hmap_dims[0], m.hmap_dims[1] = n, n; ctx.set_map(m)
+    ctx.upload(0, runs["drops/in/H"])
+    ctx.upload(2, np.zeros_like(runs["drops/in/H"]))
+    for s in range(1, 6):      # a spawn time for which no two droplets share a texel: the result is order-free
+        ctx.dispatch_particle(_time(int(runs["drops/t0"]) + s), True)
+    assert np.asarray(ctx.download_particles()).tobytes() == runs["drops/step5/particles"].tobytes()
+    assert_bit_equal(ctx.download(0), runs["drops/step5/H"], "droplets: heightmap")
+    assert_bit_equal(ctx.download(2), runs["drops/step5/M"], "droplets: momentum map")
+    ctx.close()

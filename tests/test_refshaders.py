@@ -66,6 +66,29 @@ def test_rain_matches_the_reference_shader(wet):
     _compare(ref, orc, "rain", ("heightmap",))
 
 
+@pytest.mark.parametrize("variant", ["default", "uplift_terrace", "round_slope_warp2", "exp_power_warp1"])
+def test_heightmap_init_matches_the_reference_shader(variant):
+    """heightmap.glsl (State::World::gen_heightmap, src/state.cpp:116-147) with the noise functions it reaches
+    (simplex_noise.glsl: hash, noised, perlfbm, erosion_perlfbm, gln_simplex, gln_sfbm) in every mask / warp /
+    terrace branch, against the oracle."""
+    n = 64
+    orc = oracle.World(n, seed=SEED)
+    m = orc.map
+    if variant == "uplift_terrace":
+        m.uplift, m.terrace, m.terrace_scale = 1, 6, 0.5
+    elif variant == "round_slope_warp2":
+        m.mask_round, m.mask_slope, m.domain_warp = 1, 1, 2
+    elif variant == "exp_power_warp1":
+        m.mask_exp, m.mask_power, m.domain_warp, m.uplift = 1, 1, 1, 1
+    ref = _ref_from(orc)
+    ref.gen_heightmap()
+    orc.gen_heightmap()
+    _compare(ref, orc, f"heightmap init ({variant})", ("heightmap", "flux", "velocity", "sediment"))
+    H = orc.get(0)
+    assert H[..., 0].max() > H[..., 0].min() and (H[..., 1] > 0).all()
+    orc.close()
+
+
 @pytest.mark.parametrize("variant", ["default", "steep_fast", "thin_dirt"])
 def test_multi_step_runs_match_the_reference_shaders(variant):
     """main-loop iterations (src/main.cpp:310-321) from the generated terrain: rain when due, then the 8 dispatches"""
@@ -92,6 +115,40 @@ def test_multi_step_runs_match_the_reference_shaders(variant):
     assert orc.get(0)[..., 2].max() > 0
     if variant == "steep_fast":
         assert thermal > 0          # thermal outflow (both neighbour classes) was live
+    orc.close()
+
+
+@pytest.mark.parametrize("hmap", [64, 48])
+def test_droplet_mode_matches_the_reference_shaders(hmap):
+    """Erosion::dispatch_particle (src/erosion.cpp:132-156): particle.glsl, particle_erosion.glsl (spin lock on
+    the r32ui lock map), thermal x2, smoothing with the momentum map.  The shaders' invocations run in id order
+    here, which is the order the oracle defines for contended texels; 1024 droplets on 48^2 / 64^2 cells collide
+    constantly, so the lock path and the layer-exhaustion clamp are live.
+    hmap_dims <= map size, as in every configuration the reference can reach (main.cpp:210 makes them equal;
+    droplets die 2 cells inside hmap_dims).  With hmap_dims LARGER than the map (tried: the default (1024, 1024)
+    on this 64^2 map) droplets walk off the map and deposit momentum on its border texels, which smoothing.glsl
+    never rewrites (early return, :27-33): the reference then reads back whatever the other ping-pong texture
+    held two steps earlier, while the oracle and the product define those texels as 0 (oracle/hg_oracle.c,
+    smooth_pass) -- the two agree for 8 steps and then part; that configuration is outside the contract."""
+    n, count = 64, 1024
+    orc = oracle.World(n, particle_count=count, erosion_type=1, seed=SEED)
+    orc.gen_heightmap()
+    if hmap:
+        orc.map.hmap_dims[0], orc.map.hmap_dims[1] = hmap, hmap
+    e = oracle.ErosionData.from_buffer_copy(bytes(orc.erosion))
+    ref = refshaders.RefWorld(n, e, oracle.RainData.from_buffer_copy(bytes(orc.rain)),
+                              oracle.MapSettingsData.from_buffer_copy(bytes(orc.map)), particle_count=count)
+    for k, f in enumerate(FIELDS):
+        getattr(ref, f).read[...] = orc.get(k)
+    for s in range(1, 13):
+        t = float(np.float32(s) * np.float32(DT_TIME))
+        rain = s < 9                                   # later steps: no respawn, droplets die out
+        ref.dispatch_particle(t, rain)
+        orc.dispatch_particle(t, rain)
+        assert ref.particle_buffer[:count * 48].tobytes() == orc.particles().tobytes(), f"droplets differ after step {s}"
+        _compare(ref, orc, f"droplet step {s}", ("heightmap", "velocity"))
+    p = orc.particles()
+    assert (p["iters"] > 0).any() and (p["to_kill"] != 0).any()
     orc.close()
 
 
