@@ -148,13 +148,17 @@ def generate():
                      "        gl_GlobalInvocationID.x = id; gl_GlobalInvocationID.y = 0; gl_GlobalInvocationID.z = 0;\n"
                      "        gl_GlobalInvocationID.xy = uvec2(id, 0);\n"
                      "        shader_main();\n    }\n    return 0;\n}\n")
+        # grid dispatch: invocations are independent (each writes only its own texel of the write images), so rows run
+        # on all host threads; the built-in variables are thread_local
         parts.append("static int run(int W, int H) {\n"
-                     "    gl_WorkGroupSize.x = WRKGRP_SIZE_X; gl_WorkGroupSize.y = WRKGRP_SIZE_Y; gl_WorkGroupSize.z = 1;\n"
-                     "    gl_NumWorkGroups.x = W / WRKGRP_SIZE_X; gl_NumWorkGroups.y = H / WRKGRP_SIZE_Y; gl_NumWorkGroups.z = 1;\n"
-                     "    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {\n"
-                     "        gl_GlobalInvocationID.x = x; gl_GlobalInvocationID.y = y; gl_GlobalInvocationID.z = 0;\n"
-                     "        gl_GlobalInvocationID.xy = uvec2(x, y);\n"
-                     "        shader_main();\n    }\n    return 0;\n}\n")
+                     "    _Pragma(\"omp parallel for schedule(static)\")\n"
+                     "    for (int y = 0; y < H; y++) {\n"
+                     "        gl_WorkGroupSize.x = WRKGRP_SIZE_X; gl_WorkGroupSize.y = WRKGRP_SIZE_Y; gl_WorkGroupSize.z = 1;\n"
+                     "        gl_NumWorkGroups.x = W / WRKGRP_SIZE_X; gl_NumWorkGroups.y = H / WRKGRP_SIZE_Y; gl_NumWorkGroups.z = 1;\n"
+                     "        for (int x = 0; x < W; x++) {\n"
+                     "            gl_GlobalInvocationID.x = x; gl_GlobalInvocationID.y = y; gl_GlobalInvocationID.z = 0;\n"
+                     "            gl_GlobalInvocationID.xy = uvec2(x, y);\n"
+                     "            shader_main();\n        }\n    }\n    return 0;\n}\n")
         parts.append("static_assert(sizeof(Erosion_data) == 96 && sizeof(Rain_data) == 20 && sizeof(Map_settings_data) == 96 && sizeof(Particle) == 48, \"std140 / std430 images of the blocks\");\n")
         parts.append("} }\n")
         table.append(shader)
@@ -182,7 +186,7 @@ def build():
         if "--keep" in sys.argv:
             import shutil
             shutil.copy(cpp, "/tmp/ref_shaders.cpp")
-        cmd = ["g++", "-std=c++20", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared",
+        cmd = ["g++", "-std=c++20", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-fno-strict-aliasing", "-fopenmp", "-ftls-model=initial-exec", "-fPIC", "-shared",
                "-Wno-narrowing", "-I", HERE, "-o", OUT, cpp, "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
