@@ -188,11 +188,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
-    return {"workload": f"4096x{4096 * n} virtual-pipe + thermal grid erosion, wet variant (rain period {RAIN_PERIOD}), "
-                        f"{'single GPU (BASELINE config[1])' if n == 1 else f'{n} row slabs of 4096 rows, NVLink halo push per step'}",
-            "map": [4096, 4096 * n], "rows_per_gpu": 4096, "rain_period": RAIN_PERIOD, "seed": SEED,
-            "l2": "working set 604 MB per plane set per GPU > 126 MB L2, no flush needed",
+def workload_config(n, W=4096, rows=4096):
+    mb = 36 * W * rows / 1e6
+    return {"workload": f"{W}x{rows * n} virtual-pipe + thermal grid erosion, wet variant (rain period {RAIN_PERIOD}), "
+                        f"{'single GPU' + (' (BASELINE config[1])' if (W, rows) == (4096, 4096) else '') if n == 1 else f'{n} row slabs of {rows} rows, NVLink halo push per step'}",
+            "map": [W, rows * n], "rows_per_gpu": rows, "rain_period": RAIN_PERIOD, "seed": SEED,
+            "l2": f"working set {mb:.0f} MB per plane set per GPU > 126 MB L2, no flush needed",
             "parallelism": f"row-slab x{n}" if n > 1 else "none"}
 
 
@@ -204,6 +205,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # the other BASELINE configs, for manual runs (the driver uses the defaults): e.g. --width 16384 --rows-per-gpu 2048
+    # --gpus 8 is 16384^2 strong-scaled over 8 slabs, --width 65536 --rows-per-gpu 8192 --gpus 8 --e2e-steps 0 is 65536^2
+    ap.add_argument("--width", type=int, default=4096)
+    ap.add_argument("--rows-per-gpu", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -223,7 +228,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    W, rows = 4096, 4096
+    W, rows = args.width, args.rows_per_gpu
     H = rows * n
     ctx = Context(W, H, device=local, row0=rank * rows, rows=rows)
     m = ctx.get_map(); m.seed = SEED; ctx.set_map(m)
@@ -291,29 +296,33 @@ def main():
     # images (the reference's texture format), steps, and downloads H, F, S into a second set.
     # hg_step_host_async pipelines consecutive steps over copy streams (PCIe is full duplex).
     fields = (_lib.FIELD_HEIGHTMAP, _lib.FIELD_FLUX, _lib.FIELD_SEDIMENT)
+    if args.e2e_steps <= 0:          # manual runs of the very large configs: no host images
+        fields = ()
     pins = [PinnedBuffer((rows, W, 4)) for _ in fields]
     pouts = [PinnedBuffer((rows, W, 4)) for _ in fields]
     for f, p in zip(fields, pins):
         ctx.download(f, p.array)
     ins, outs = [p.array for p in pins], [p.array for p in pouts]
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    for _ in range(2):      # warm the staging path
-        ctx.step_host_async(ins, outs)
-    barrier()
-    ctx.timer_start()
-    for _ in range(e2e_steps):
-        ctx.step_host_async(ins, outs)
-    e_ms = ctx.timer_stop()     # waits for the last download
-    barrier()
+    e_ms = float("nan")
+    if fields:
+        for _ in range(2):      # warm the staging path
+            ctx.step_host_async(ins, outs)
+        barrier()
+        ctx.timer_start()
+        for _ in range(e2e_steps):
+            ctx.step_host_async(ins, outs)
+        e_ms = ctx.timer_stop()     # waits for the last download
+        barrier()
     if n > 1:
         import torch
         te = torch.tensor([e_ms], device="cuda")
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e_ms = float(te.item())
-    e2e_val = cells / (e_ms / e2e_steps * 1e-3) / 1e9
+    e2e_val = cells / (e_ms / e2e_steps * 1e-3) / 1e9 if fields else None
     bytes_dir = len(fields) * rows * W * 16
     e2e = {"value": e2e_val, "unit": "Gcell-steps/s", "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
-           "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps,
+           "steps": e2e_steps, "ms_per_step": e_ms / e2e_steps if fields else None,
            "what": "per step: hg_step_host_async = upload H,F,S from pinned RGBA32F host images, Erosion::dispatch_grid, "
                    "download H,F,S to a second pinned set; consecutive steps pipelined over 3 streams"}
     halo_errors = ctx.slab_errors()
@@ -321,7 +330,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Gcell-steps/s", "n_gpus": n, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(n, W, rows),
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "far_fetch_cells_per_step": far / args.steps, "halo_errors": halo_errors}
         if n == 1 and not args.no_cpu_baseline:
