@@ -39,6 +39,8 @@ static void free_ctx(hg_ctx* c) {
     if (c->ev_down) cudaEventDestroy(c->ev_down);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->far_list) cudaFree(c->far_list);
+    if (c->plan[0]) cudaFree(c->plan[0]);
+    if (c->cta_ns) cudaFree(c->cta_ns);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -120,6 +122,7 @@ extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0,
     c->tune_variant = -1;
     if (const char* e = getenv("HG_FUSED_SEG")) c->tune_seg = atoi(e);   // tuning aids
     if (const char* e = getenv("HG_FUSED_VARIANT")) c->tune_variant = atoi(e);
+    if (const char* e = getenv("HG_FUSED_BALANCE")) c->no_balance = atoi(e) == 0;
     refresh_params(c);
     if (create_impl(c) != HG_OK) { free_ctx(c); return nullptr; }
     return c;

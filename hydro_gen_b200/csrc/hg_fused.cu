@@ -17,6 +17,7 @@
 // All arithmetic is the shared per-cell code of hg_cell.cuh: results are bit-identical to
 // the PASSES schedule and to the CPU oracle.
 #include <cuda.h>
+#include <vector>
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
 
@@ -245,13 +246,22 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
     const bool hydro = threadIdx.x < NT;
     const int tid = hydro ? threadIdx.x : threadIdx.x - NT;
-    const int strip = blockIdx.x % K.nstrips, segi = blockIdx.x / K.nstrips;
+    int strip, gy0, gy1;
+    if (K.plan) {           // balanced partition (hg_plan_*): this CTA's strip and rows come from the plan
+        const HgPlanItem it = K.plan[blockIdx.x];
+        strip = it.strip; gy0 = it.gy0; gy1 = it.gy1;
+    } else {
+        const int segi = blockIdx.x / K.nstrips;
+        strip = blockIdx.x % K.nstrips;
+        gy0 = K.row0 + segi * K.seg;
+        gy1 = min(gy0 + K.seg, K.row0 + K.rows);
+    }
+    unsigned long long t_start = 0;
+    if (K.cta_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
     const int x = x0 + tid;
     const bool xin = x >= 0 && x < K.W;
     const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
-    const int gy0 = K.row0 + segi * K.seg;
-    const int gy1 = min(gy0 + K.seg, K.row0 + K.rows);
     const HgFusedPlan pl = hg_fused_plan(gy0, gy1, K.H);
     const unsigned pitch = (unsigned)K.pitch;
     unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
@@ -288,6 +298,11 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
 #undef HG_ROW_H
+        if (K.cta_ns && threadIdx.x == 0) {       // the last barrier has passed: both groups are done with their rows
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
+        }
     } else {
         if (RH != RT) reg_inc<RT>();
 #define HG_ROW_T(FREEFLAG)                                                                                           \
@@ -300,6 +315,108 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
 #undef HG_ROW_T
+    }
+}
+
+// ------------------------------------------------------------------ balanced partition
+// All CTAs of a step are resident at once (one wave, 3 per SM), so the step ends when the SLOWEST CTA
+// ends.  With equal segments of rows that was 0.69 ms at 4096^2 while the mean CTA took 0.55 ms: the
+// cost of a row depends on the terrain (the thermal outflow path is taken only where a cell is marked)
+// and on the strip (the ones overhanging the map edge).  Terrain changes slowly, so the durations
+// the CTAs of one step report are a good forecast for the next: this kernel re-cuts every strip into
+// row segments of equal FORECAST cost, handing a strip a share of the n_cta segments proportional to
+// its total.  One thread per strip; the cost inside an old segment is taken as uniform.  Any partition
+// gives the same bits (segments only decide who computes a row), so a poor forecast costs time only.
+struct PlanArgs {
+    const HgPlanItem* old_plan; const unsigned* cta_ns; HgPlanItem* new_plan;
+    int n_cta, nstrips, row0, rows, min_rows;
+    int equal_counts;      // every strip keeps n_cta / nstrips segments; only the cuts inside a strip move
+};
+__global__ void __launch_bounds__(512) k_plan_segments(PlanArgs A) {
+    __shared__ float strip_cost[256], frac[256], total_s;
+    __shared__ int strip_first[257], new_n[256], new_first[257], given_s;
+    const int t = threadIdx.x;
+    // old segments are grouped by strip, in row order: a strip starts where the strip index changes
+    for (int b = t; b < A.n_cta; b += blockDim.x)
+        if (b == 0 || A.old_plan[b].strip != A.old_plan[b - 1].strip) strip_first[A.old_plan[b].strip] = b;
+    if (t == 0) strip_first[A.nstrips] = A.n_cta;
+    __syncthreads();
+    if (t < A.nstrips) {
+        float c = 0.0f;
+        for (int k = strip_first[t]; k < strip_first[t + 1]; k++) c += fmaxf(1.0f, (float)A.cta_ns[k]);
+        strip_cost[t] = c;
+    }
+    __syncthreads();
+    if (t == 0) {
+        float total = 0.0f;
+        for (int k = 0; k < A.nstrips; k++) total += strip_cost[k];
+        total_s = total;
+    }
+    __syncthreads();
+    // segments per strip: proportional to cost (largest remainders get the left-over ones), at least 1
+    const int cap = max(1, A.rows / A.min_rows);
+    if (t < A.nstrips) {
+        const float share = A.equal_counts ? (float)(A.n_cta / A.nstrips) : (float)A.n_cta * strip_cost[t] / total_s;
+        int n = (int)floorf(share);
+        frac[t] = share - (float)n;
+        new_n[t] = min(max(n, 1), cap);
+    }
+    __syncthreads();
+    if (t == 0) {
+        int g = 0;
+        for (int k = 0; k < A.nstrips; k++) g += new_n[k];
+        given_s = g;
+    }
+    __syncthreads();
+    if (t < A.nstrips && given_s < A.n_cta) {
+        int rank = 0;                                   // strips with a larger remainder than mine
+        for (int k = 0; k < A.nstrips; k++) rank += (frac[k] > frac[t] || (frac[k] == frac[t] && k < t)) ? 1 : 0;
+        if (rank < A.n_cta - given_s && new_n[t] < cap) new_n[t] += 1;
+    }
+    __syncthreads();
+    if (t == 0) {       // whatever the clamps left over (rare): one at a time, where the cost per segment is largest / smallest
+        int g = 0;
+        for (int k = 0; k < A.nstrips; k++) g += new_n[k];
+        while (g != A.n_cta) {
+            int best = -1; float best_v = 0.0f;
+            for (int k = 0; k < A.nstrips; k++) {
+                if (g < A.n_cta ? new_n[k] >= cap : new_n[k] <= 1) continue;
+                const float v = strip_cost[k] / (float)(g < A.n_cta ? new_n[k] : new_n[k] - 1);
+                if (best < 0 || (g < A.n_cta ? v > best_v : v < best_v)) { best = k; best_v = v; }
+            }
+            if (best < 0) break;
+            new_n[best] += g < A.n_cta ? 1 : -1;
+            g += g < A.n_cta ? 1 : -1;
+        }
+        int b = 0;
+        for (int k = 0; k < A.nstrips; k++) { new_first[k] = b; b += new_n[k]; }
+        new_first[A.nstrips] = b;
+    }
+    __syncthreads();
+    if (t < A.nstrips) {
+        const int s = t, n = new_n[s], first = new_first[s], old_last = strip_first[s + 1] - 1;
+        const float target = strip_cost[s] / (float)n;
+        int k = strip_first[s];                      // old segment being consumed
+        float before = 0.0f;                         // cost of this strip's old segments before k
+        int y_prev = A.row0;
+        for (int m = 1; m <= n; m++) {
+            int y;
+            if (m == n) {
+                y = A.row0 + A.rows;
+            } else {
+                const float want = target * (float)m;
+                while (k < old_last && before + fmaxf(1.0f, (float)A.cta_ns[k]) < want) { before += fmaxf(1.0f, (float)A.cta_ns[k]); k++; }
+                const HgPlanItem o = A.old_plan[k];
+                float f = (want - before) / fmaxf(1.0f, (float)A.cta_ns[k]);      // the cost inside an old segment is taken as uniform
+                f = fminf(fmaxf(f, 0.0f), 1.0f);
+                y = o.gy0 + (int)(f * (float)(o.gy1 - o.gy0) + 0.5f);
+                y = max(y, y_prev + A.min_rows);                                  // every segment at least min_rows tall,
+                y = min(y, A.row0 + A.rows - (n - m) * A.min_rows);               // also the ones still to come
+            }
+            HgPlanItem it; it.strip = s; it.gy0 = y_prev; it.gy1 = y; it.pad = 0;
+            A.new_plan[first + m - 1] = it;
+            y_prev = y;
+        }
     }
 }
 
@@ -370,7 +487,7 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     int rc = make_tmap(c, src_set, NT, &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
-    k_fused_ws<NT, MINB, RH, RT><<<K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
+    k_fused_ws<NT, MINB, RH, RT><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
@@ -447,6 +564,52 @@ int hg_launch_fused_step(hg_ctx* c) {
             if (cost < best) { best = cost; seg = sg; }
         }
     }
+    // Balanced partition (default for the warp-specialised kernel when the slab is big enough to fill the GPU):
+    // n_cta = 3 CTAs on every SM, cut per strip by the forecast of k_plan_segments.  HG_FUSED_SEG or
+    // HG_FUSED_BALANCE=0 keep the uniform segments.
+    bool balanced = false;
+    if (v == 5 && c->tune_seg <= 0 && !c->no_balance) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        // Only with at least six segments per strip: with fewer (16384 columns: 3.1 per strip) one segment more or
+        // less is too coarse a step, and moving only the cuts inside a strip was measured 5 % SLOWER than uniform
+        // segments there (CTAs of 5000 rows already average the terrain; the forecast then mostly carries noise).
+        const int min_rows = 48;
+        const bool equal_counts = false;
+        const int n_cta = 3 * sms;
+        if (n_cta / nstrips >= 6 && (long long)nstrips * (c->g.rows / min_rows) >= 2LL * n_cta) {
+            if (!c->plan[0]) {      // first use: uniform cut into n_cta pieces (strip k gets n_cta/nstrips, the first few one more)
+                HG_CUDA(cudaMalloc(&c->plan[0], 2 * n_cta * sizeof(HgPlanItem)));
+                c->plan[1] = c->plan[0] + n_cta;
+                HG_CUDA(cudaMalloc(&c->cta_ns, n_cta * sizeof(unsigned)));
+                std::vector<HgPlanItem> h;
+                for (int k = 0; k < nstrips; k++) {
+                    const int n = n_cta / nstrips + (k < n_cta % nstrips ? 1 : 0);
+                    for (int m = 0; m < n; m++) {
+                        HgPlanItem it;
+                        it.strip = k; it.pad = 0;
+                        it.gy0 = c->g.row0 + (int)((long long)c->g.rows * m / n);
+                        it.gy1 = c->g.row0 + (int)((long long)c->g.rows * (m + 1) / n);
+                        h.push_back(it);
+                    }
+                }
+                HG_CUDA(cudaMemcpyAsync(c->plan[0], h.data(), h.size() * sizeof(HgPlanItem), cudaMemcpyHostToDevice, c->stream));
+                HG_CUDA(cudaStreamSynchronize(c->stream));      // h goes out of scope
+                c->plan_cur = 0; c->plan_n = n_cta; c->plan_valid = false;
+            }
+            if (c->plan_valid) {    // durations of the previous step -> this step's cut
+                PlanArgs PA{c->plan[c->plan_cur], c->cta_ns, c->plan[c->plan_cur ^ 1], n_cta, nstrips, c->g.row0, c->g.rows, min_rows, equal_counts ? 1 : 0};
+                k_plan_segments<<<1, 512, 0, c->stream>>>(PA);
+                HG_LAUNCH_CHECK(c);
+                c->plan_cur ^= 1;
+            }
+            K.plan = c->plan[c->plan_cur];
+            K.cta_ns = c->cta_ns;
+            c->plan_valid = true;
+            balanced = true;
+        }
+    }
+    (void)balanced;
     int rc;
     switch (v) {
     case 0: rc = launch_main<128, 4>(c, K, seg, c->ri[0]); break;

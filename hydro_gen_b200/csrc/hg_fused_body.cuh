@@ -93,6 +93,8 @@ template <int NT> struct HgRings {
     static constexpr int TOTAL = TOTAL_BYTES / 4;    // 74 * E floats
 };
 
+struct HgPlanItem { int strip, gy0, gy1, pad; };
+
 struct HgFusedK {
     const float* src[HGF_NPL];
     float* dst[HGF_NPL];
@@ -100,6 +102,10 @@ struct HgFusedK {
     int seg, nstrips;
     unsigned* far_list;                  // local linear cell indices (row - row0) * W + x
     unsigned long long* far_count;       // this step's counter
+    // balanced partition (k_fused_ws): CTA b works on strip plan[b].x, rows [plan[b].y, plan[b].z) and reports its
+    // duration in cta_ns[b]; null = uniform segments of `seg` rows
+    const HgPlanItem* plan;
+    unsigned* cta_ns;
     HgStepParams P;
 };
 

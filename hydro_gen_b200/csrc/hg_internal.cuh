@@ -80,6 +80,12 @@ struct hg_ctx {
     int far_parity;
     int tune_variant;          // CTA shape of the fused kernel; -1 = default (HG_FUSED_VARIANT env at create)
     int tune_seg;              // rows per CTA of the fused kernel; 0 = automatic (HG_FUSED_SEG env at create)
+    // balanced partition of the fused step (hg_fused.cu, k_plan_segments): two plans (this step's / next step's), the
+    // durations the CTAs reported, which plan is current; no_balance = HG_FUSED_BALANCE=0
+    struct HgPlanItem* plan[2];
+    unsigned* cta_ns;
+    int plan_cur, plan_n;
+    bool plan_valid, no_balance;
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
     // pipelined host step (hg_step_host_async): copy streams, full-size staging, ordering events

