@@ -9,7 +9,8 @@ from hydro_gen_b200 import Context, slabs
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-W, H, STEPS = 1024, 512 * world, 48
+# MGPU_W / MGPU_ROWS: e.g. 4096 / 1280 makes every slab (and the whole map) large enough for the balanced partition
+W, H, STEPS = int(os.environ.get("MGPU_W", 1024)), int(os.environ.get("MGPU_ROWS", 512)) * world, int(os.environ.get("MGPU_STEPS", 48))
 row0, rows = slabs.slab_rows(H, world, rank)
 
 def setup(ctx):
