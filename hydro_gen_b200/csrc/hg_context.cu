@@ -39,6 +39,9 @@ static void free_ctx(hg_ctx* c) {
     if (c->ev_down) cudaEventDestroy(c->ev_down);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->far_list) cudaFree(c->far_list);
+    if (c->plan_stream) { cudaStreamSynchronize(c->plan_stream); cudaStreamDestroy(c->plan_stream); }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
     if (c->plan[0]) cudaFree(c->plan[0]);
     if (c->cta_ns) cudaFree(c->cta_ns);
     if (c->ev0) cudaEventDestroy(c->ev0);

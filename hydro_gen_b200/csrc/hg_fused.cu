@@ -568,6 +568,7 @@ int hg_launch_fused_step(hg_ctx* c) {
     // n_cta = 3 CTAs on every SM, cut per strip by the forecast of k_plan_segments.  HG_FUSED_SEG or
     // HG_FUSED_BALANCE=0 keep the uniform segments.
     bool balanced = false;
+    PlanArgs plan_args{};
     if (v == 5 && c->tune_seg <= 0 && !c->no_balance) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -575,7 +576,6 @@ int hg_launch_fused_step(hg_ctx* c) {
         // less is too coarse a step, and moving only the cuts inside a strip was measured 5 % SLOWER than uniform
         // segments there (CTAs of 5000 rows already average the terrain; the forecast then mostly carries noise).
         const int min_rows = 48;
-        const bool equal_counts = false;
         const int n_cta = 3 * sms;
         if (n_cta / nstrips >= 6 && (long long)nstrips * (c->g.rows / min_rows) >= 2LL * n_cta) {
             if (!c->plan[0]) {      // first use: uniform cut into n_cta pieces (strip k gets n_cta/nstrips, the first few one more)
@@ -597,19 +597,16 @@ int hg_launch_fused_step(hg_ctx* c) {
                 HG_CUDA(cudaStreamSynchronize(c->stream));      // h goes out of scope
                 c->plan_cur = 0; c->plan_n = n_cta; c->plan_valid = false;
             }
-            if (c->plan_valid) {    // durations of the previous step -> this step's cut
-                PlanArgs PA{c->plan[c->plan_cur], c->cta_ns, c->plan[c->plan_cur ^ 1], n_cta, nstrips, c->g.row0, c->g.rows, min_rows, equal_counts ? 1 : 0};
-                k_plan_segments<<<1, 512, 0, c->stream>>>(PA);
-                HG_LAUNCH_CHECK(c);
-                c->plan_cur ^= 1;
+            if (c->plan_valid) {    // the cut for this step was made on the side stream while the previous step finished
+                HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_plan, 0));
+                c->plan_valid = false;
             }
             K.plan = c->plan[c->plan_cur];
             K.cta_ns = c->cta_ns;
-            c->plan_valid = true;
             balanced = true;
+            plan_args = PlanArgs{c->plan[c->plan_cur], c->cta_ns, c->plan[c->plan_cur ^ 1], n_cta, nstrips, c->g.row0, c->g.rows, min_rows, 0};
         }
     }
-    (void)balanced;
     int rc;
     switch (v) {
     case 0: rc = launch_main<128, 4>(c, K, seg, c->ri[0]); break;
@@ -624,6 +621,22 @@ int hg_launch_fused_step(hg_ctx* c) {
     default: rc = launch_ws<128, 4, 56, 72>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
+    if (balanced) {
+        // durations of this step -> the next step's cut, on a side stream beside the fix-up kernel (both are tiny
+        // and latency-bound; the next step kernel waits for ev_plan)
+        if (!c->plan_stream) {
+            HG_CUDA(cudaStreamCreateWithFlags(&c->plan_stream, cudaStreamNonBlocking));
+            HG_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+            HG_CUDA(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
+        }
+        HG_CUDA(cudaEventRecord(c->ev_main, c->stream));
+        HG_CUDA(cudaStreamWaitEvent(c->plan_stream, c->ev_main, 0));
+        k_plan_segments<<<1, 512, 0, c->plan_stream>>>(plan_args);
+        HG_LAUNCH_CHECK(c);
+        HG_CUDA(cudaEventRecord(c->ev_plan, c->plan_stream));
+        c->plan_cur ^= 1;
+        c->plan_valid = true;
+    }
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);
     for (int f = 0; f < 4; f++) if (f != 2) c->ri[f] ^= 1;   // H, F, S flip once per fused step; V is not stored

@@ -85,7 +85,9 @@ struct hg_ctx {
     struct HgPlanItem* plan[2];
     unsigned* cta_ns;
     int plan_cur, plan_n;
-    bool plan_valid, no_balance;
+    bool plan_valid, no_balance;      // plan_valid: plan[plan_cur] is being written on plan_stream (wait for ev_plan)
+    cudaStream_t plan_stream;
+    cudaEvent_t ev_main, ev_plan;
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
     // pipelined host step (hg_step_host_async): copy streams, full-size staging, ordering events
