@@ -261,9 +261,8 @@ def main():
         time.sleep(0.25)
     barrier()
     launches0 = ctx.launch_count
-    ctx.timer_start()
-    ctx.run(args.steps, t, DT_TIME, True)
-    ms = ctx.timer_stop()
+    # the timed region: K steps between two CUDA events on the step stream, plus one event pair around every fused step kernel
+    ms, k_ms = ctx.run_profiled(args.steps, t, DT_TIME, True)
     barrier()
     launches = ctx.launch_count - launches0
     t += args.steps * DT_TIME
@@ -278,8 +277,7 @@ def main():
     cells = W * H
     value = cells / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant kernel: its own duration, CUDA events around that launch alone
-    k_ms = ctx.profile_fused(20)
+    # roofline of the dominant kernel: its average duration over the timed region (CUDA events around every launch)
     if n > 1:
         import torch
         tk = torch.tensor([k_ms], device="cuda")

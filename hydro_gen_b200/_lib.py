@@ -98,6 +98,7 @@ SYMBOLS = {
     "hg_timer_start": (_i, [_vp]),
     "hg_timer_stop": (_i, [_vp, _fp]),
     "hg_profile_fused": (_i, [_vp, _u, _fp]),
+    "hg_run_profiled": (_i, [_vp, _u, _f, _f, _i, _fp, _fp]),
     "hg_launch_count": (C.c_uint64, [_vp]),
     "hg_far_fetch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "hg_slab_export_handle": (_i, [_vp, C.POINTER(SlabExport)]),

@@ -177,6 +177,12 @@ class Context:
     def timer_stop(self):
         ms = C.c_float(); check(self.L.hg_timer_stop(self.h, C.byref(ms))); return ms.value
 
+    def run_profiled(self, n_steps, time0=0.0, dtime=0.015, should_rain=True):
+        """run() timed on the device: returns (ms of the whole run, average ms of the fused step kernel inside it)"""
+        k, tot = C.c_float(), C.c_float()
+        check(self.L.hg_run_profiled(self.h, int(n_steps), float(time0), float(dtime), int(should_rain), C.byref(k), C.byref(tot)))
+        return tot.value, k.value
+
     def profile_fused(self, n_steps):
         ms = C.c_float(); check(self.L.hg_profile_fused(self.h, int(n_steps), C.byref(ms))); return ms.value
 

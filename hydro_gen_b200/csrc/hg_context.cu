@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
 #include "hg_internal.cuh"
 
 static thread_local char g_err[512] = "";
@@ -556,10 +557,11 @@ extern "C" int hg_dispatch_particle(hg_ctx* c, float time, int should_rain) {
 }
 
 // src/main.cpp:310-324
-extern "C" int hg_run(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int should_rain) {
-    HG_CHECK_CTX(c);
+// ev: null, or 2 * n_steps events: the pair (2k, 2k+1) is recorded around the fused step kernel of iteration k
+static int run_steps(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int should_rain, cudaEvent_t* ev) {
     for (uint32_t k = 0; k < n_steps; k++) {
         float time = time0 + (float)k * dtime;
+        if (ev) { c->prof_ev0 = ev[2 * k]; c->prof_ev1 = ev[2 * k + 1]; }
         c->erosion_steps++;
         int rc;
         if (c->erosion_type == HG_GRID) {
@@ -571,9 +573,43 @@ extern "C" int hg_run(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int
         } else {
             rc = hg_dispatch_particle(c, time, should_rain);
         }
+        c->prof_ev0 = c->prof_ev1 = nullptr;
         if (rc) return rc;
     }
     return HG_OK;
+}
+
+extern "C" int hg_run(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int should_rain) {
+    HG_CHECK_CTX(c);
+    return run_steps(c, n_steps, time0, dtime, should_rain, nullptr);
+}
+
+// hg_run that also times the fused step kernel of every iteration (one CUDA event pair per iteration on the
+// handle's stream, no host synchronisation inside the run) and returns the average: the kernel's duration
+// INSIDE a real run, rain, fix-up and planner kernels around it as usual.  Blocking.
+extern "C" int hg_run_profiled(hg_ctx* c, uint32_t n_steps, float time0, float dtime, int should_rain, float* avg_kernel_ms, float* total_ms) {
+    HG_CHECK_CTX(c);
+    if (c->erosion_type != HG_GRID || c->schedule != HG_SCHEDULE_FUSED || !n_steps) { hg_set_error("hg_run_profiled needs a grid context on the FUSED schedule"); return HG_ERR_STATE; }
+    std::vector<cudaEvent_t> ev(2 * (size_t)n_steps, nullptr);
+    int rc = HG_OK;
+    for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) { hg_set_error("cudaEventCreate failed"); rc = HG_ERR_CUDA; break; }
+    if (rc == HG_OK) {
+        cudaEventRecord(c->ev0, c->stream);         // the whole run, on the device: from before the first launch ...
+        rc = run_steps(c, n_steps, time0, dtime, should_rain, ev.data());
+        cudaEventRecord(c->ev1, c->stream);         // ... to after the last one
+    }
+    if (rc == HG_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) { hg_set_error("cudaStreamSynchronize failed"); rc = HG_ERR_CUDA; }
+    double total = 0.0;
+    if (rc == HG_OK) {
+        for (uint32_t k = 0; k < n_steps; k++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]) == cudaSuccess) total += ms;
+        }
+    }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (avg_kernel_ms) *avg_kernel_ms = (float)(total / n_steps);
+    if (total_ms) { float ms = 0.0f; if (rc == HG_OK) cudaEventElapsedTime(&ms, c->ev0, c->ev1); *total_ms = ms; }
+    return rc;
 }
 extern "C" int hg_get_steps(hg_ctx* c, uint32_t* s) { HG_CHECK_CTX(c); if (!s) return HG_ERR_INVALID; *s = c->erosion_steps; return HG_OK; }
 extern "C" int hg_set_steps(hg_ctx* c, uint32_t s) { HG_CHECK_CTX(c); c->erosion_steps = s; return HG_OK; }

@@ -153,6 +153,11 @@ int hg_timer_stop(hg_ctx* ctx, float* elapsed_ms);
 /* Average duration of the fused step kernel alone over n_steps real steps (CUDA events around
  * that one launch on the handle's stream); the roofline figure of bench.py.  Blocking. */
 int hg_profile_fused(hg_ctx* ctx, uint32_t n_steps, float* avg_kernel_ms);
+/* hg_run (src/main.cpp:310-324) that also times the fused step kernel of every iteration with one CUDA event pair per
+ * iteration on the handle's stream, without synchronising inside the run: the kernel's average duration inside a real
+ * run (bench.py's roofline figure, taken over its timed region), and the duration of the whole run between two events
+ * on the stream (before the first launch, after the last).  Blocking. */
+int hg_run_profiled(hg_ctx* ctx, uint32_t n_steps, float time0, float dtime, int should_rain, float* avg_kernel_ms, float* total_ms);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 uint64_t hg_launch_count(hg_ctx* ctx);
 /* Cells whose sediment back-trace left the on-chip window and took the far-fetch path,
