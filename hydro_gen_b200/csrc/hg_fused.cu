@@ -16,6 +16,11 @@
 //
 // All arithmetic is the shared per-cell code of hg_cell.cuh: results are bit-identical to
 // the PASSES schedule and to the CPU oracle.
+//
+// Kernels in this file: k_fused_ws (the default: hydraulic and thermal stages on two warp groups of
+// one CTA, three CTAs per SM), k_fused_step (the single-group form, a tuning variant), k_far_fixup,
+// and k_plan_segments (re-cuts the strips into row segments of equal forecast cost for the next
+// step, from the durations the CTAs of this step reported).
 #include <cuda.h>
 #include <vector>
 #include "hg_internal.cuh"
