@@ -25,6 +25,7 @@
 #include <vector>
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
+#include "hg_plan.cuh"
 
 #ifndef HG_FREE_UNROLL
 #define HG_FREE_UNROLL 1
@@ -335,11 +336,12 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
 struct PlanArgs {
     const HgPlanItem* old_plan; const unsigned* cta_ns; HgPlanItem* new_plan;
     int n_cta, nstrips, row0, rows, min_rows;
-    int equal_counts;      // every strip keeps n_cta / nstrips segments; only the cuts inside a strip move
 };
+// One CTA.  The arithmetic is hg_plan.cuh (shared with the CPU tests); here only the bookkeeping: where each
+// strip's old segments start, the per-strip cost sums, and one thread per strip for the cuts.
 __global__ void __launch_bounds__(512) k_plan_segments(PlanArgs A) {
     __shared__ float strip_cost[256], frac[256], total_s;
-    __shared__ int strip_first[257], new_n[256], new_first[257], given_s;
+    __shared__ int strip_first[257], new_n[256], new_first[257], left_s;
     const int t = threadIdx.x;
     // old segments are grouped by strip, in row order: a strip starts where the strip index changes
     for (int b = t; b < A.n_cta; b += blockDim.x)
@@ -348,81 +350,39 @@ __global__ void __launch_bounds__(512) k_plan_segments(PlanArgs A) {
     __syncthreads();
     if (t < A.nstrips) {
         float c = 0.0f;
-        for (int k = strip_first[t]; k < strip_first[t + 1]; k++) c += fmaxf(1.0f, (float)A.cta_ns[k]);
+        for (int k = strip_first[t]; k < strip_first[t + 1]; k++) c += hg_plan_cost(A.cta_ns[k]);
         strip_cost[t] = c;
     }
     __syncthreads();
+    const int cap = max(1, A.rows / A.min_rows);
     if (t == 0) {
-        float total = 0.0f;
+        float total = 0.0f; 
         for (int k = 0; k < A.nstrips; k++) total += strip_cost[k];
         total_s = total;
     }
     __syncthreads();
-    // segments per strip: proportional to cost (largest remainders get the left-over ones), at least 1
-    const int cap = max(1, A.rows / A.min_rows);
-    if (t < A.nstrips) {
-        const float share = A.equal_counts ? (float)(A.n_cta / A.nstrips) : (float)A.n_cta * strip_cost[t] / total_s;
-        int n = (int)floorf(share);
-        frac[t] = share - (float)n;
-        new_n[t] = min(max(n, 1), cap);
-    }
+    if (t < A.nstrips) hg_plan_share(A.n_cta, strip_cost[t], total_s, cap, &new_n[t], &frac[t]);
     __syncthreads();
     if (t == 0) {
         int g = 0;
         for (int k = 0; k < A.nstrips; k++) g += new_n[k];
-        given_s = g;
+        left_s = A.n_cta - g;
     }
     __syncthreads();
-    if (t < A.nstrips && given_s < A.n_cta) {
-        int rank = 0;                                   // strips with a larger remainder than mine
-        for (int k = 0; k < A.nstrips; k++) rank += (frac[k] > frac[t] || (frac[k] == frac[t] && k < t)) ? 1 : 0;
-        if (rank < A.n_cta - given_s && new_n[t] < cap) new_n[t] += 1;
-    }
+    const int bonus = t < A.nstrips ? hg_plan_bonus(t, A.nstrips, frac, left_s, cap, new_n[t]) : 0;
     __syncthreads();
-    if (t == 0) {       // whatever the clamps left over (rare): one at a time, where the cost per segment is largest / smallest
-        int g = 0;
-        for (int k = 0; k < A.nstrips; k++) g += new_n[k];
-        while (g != A.n_cta) {
-            int best = -1; float best_v = 0.0f;
-            for (int k = 0; k < A.nstrips; k++) {
-                if (g < A.n_cta ? new_n[k] >= cap : new_n[k] <= 1) continue;
-                const float v = strip_cost[k] / (float)(g < A.n_cta ? new_n[k] : new_n[k] - 1);
-                if (best < 0 || (g < A.n_cta ? v > best_v : v < best_v)) { best = k; best_v = v; }
-            }
-            if (best < 0) break;
-            new_n[best] += g < A.n_cta ? 1 : -1;
-            g += g < A.n_cta ? 1 : -1;
-        }
+    if (t < A.nstrips) new_n[t] += bonus;
+    __syncthreads();
+    if (t == 0) {
+        hg_plan_repair(A.n_cta, A.nstrips, strip_cost, cap, new_n);
         int b = 0;
         for (int k = 0; k < A.nstrips; k++) { new_first[k] = b; b += new_n[k]; }
         new_first[A.nstrips] = b;
     }
     __syncthreads();
-    if (t < A.nstrips) {
-        const int s = t, n = new_n[s], first = new_first[s], old_last = strip_first[s + 1] - 1;
-        const float target = strip_cost[s] / (float)n;
-        int k = strip_first[s];                      // old segment being consumed
-        float before = 0.0f;                         // cost of this strip's old segments before k
-        int y_prev = A.row0;
-        for (int m = 1; m <= n; m++) {
-            int y;
-            if (m == n) {
-                y = A.row0 + A.rows;
-            } else {
-                const float want = target * (float)m;
-                while (k < old_last && before + fmaxf(1.0f, (float)A.cta_ns[k]) < want) { before += fmaxf(1.0f, (float)A.cta_ns[k]); k++; }
-                const HgPlanItem o = A.old_plan[k];
-                float f = (want - before) / fmaxf(1.0f, (float)A.cta_ns[k]);      // the cost inside an old segment is taken as uniform
-                f = fminf(fmaxf(f, 0.0f), 1.0f);
-                y = o.gy0 + (int)(f * (float)(o.gy1 - o.gy0) + 0.5f);
-                y = max(y, y_prev + A.min_rows);                                  // every segment at least min_rows tall,
-                y = min(y, A.row0 + A.rows - (n - m) * A.min_rows);               // also the ones still to come
-            }
-            HgPlanItem it; it.strip = s; it.gy0 = y_prev; it.gy1 = y; it.pad = 0;
-            A.new_plan[first + m - 1] = it;
-            y_prev = y;
-        }
-    }
+    if (t < A.nstrips)
+        hg_plan_cut_strip(t, new_n[t], A.old_plan + strip_first[t], A.cta_ns + strip_first[t], strip_first[t + 1] - strip_first[t],
+                          A.row0, A.rows, A.min_rows, A.new_plan + new_first[t]);
 }
 
 }  // namespace
@@ -609,7 +569,7 @@ int hg_launch_fused_step(hg_ctx* c) {
             K.plan = c->plan[c->plan_cur];
             K.cta_ns = c->cta_ns;
             balanced = true;
-            plan_args = PlanArgs{c->plan[c->plan_cur], c->cta_ns, c->plan[c->plan_cur ^ 1], n_cta, nstrips, c->g.row0, c->g.rows, min_rows, 0};
+            plan_args = PlanArgs{c->plan[c->plan_cur], c->cta_ns, c->plan[c->plan_cur ^ 1], n_cta, nstrips, c->g.row0, c->g.rows, min_rows};
         }
     }
     int rc;

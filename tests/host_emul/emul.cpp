@@ -191,3 +191,24 @@ extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt
     if (nt == 224) return fused_step_emul<224>(set, W, H, seg, ws, src, dst, far_out);
     return -1;
 }
+
+// ---- the balanced partition's arithmetic (hg_plan.cuh), as k_plan_segments applies it: plan in, plan out ----
+#include "../../hydro_gen_b200/csrc/hg_plan.cuh"
+extern "C" int emul_plan(int n_cta, int nstrips, int row0, int rows, int min_rows, const int* old_plan /* n_cta x (strip, gy0, gy1) */,
+                         const unsigned* cta_ns, int* new_plan /* n_cta x (strip, gy0, gy1) */) {
+    std::vector<HgPlanItem> old(n_cta), out(n_cta);
+    for (int b = 0; b < n_cta; b++) { old[b].strip = old_plan[3 * b]; old[b].gy0 = old_plan[3 * b + 1]; old[b].gy1 = old_plan[3 * b + 2]; old[b].pad = 0; }
+    std::vector<int> first(nstrips + 1, 0), new_n(nstrips), new_first(nstrips + 1);
+    std::vector<float> cost(nstrips, 0.0f), frac(nstrips);
+    for (int b = 0; b < n_cta; b++) if (b == 0 || old[b].strip != old[b - 1].strip) first[old[b].strip] = b;
+    first[nstrips] = n_cta;
+    for (int s = 0; s < nstrips; s++) for (int k = first[s]; k < first[s + 1]; k++) cost[s] += hg_plan_cost(cta_ns[k]);
+    hg_plan_apportion(n_cta, nstrips, cost.data(), rows / min_rows > 1 ? rows / min_rows : 1, new_n.data(), frac.data());
+    int b = 0;
+    for (int s = 0; s < nstrips; s++) { new_first[s] = b; b += new_n[s]; }
+    if (b != n_cta) return -1;
+    for (int s = 0; s < nstrips; s++)
+        hg_plan_cut_strip(s, new_n[s], old.data() + first[s], cta_ns + first[s], first[s + 1] - first[s], row0, rows, min_rows, out.data() + new_first[s]);
+    for (int k = 0; k < n_cta; k++) { new_plan[3 * k] = out[k].strip; new_plan[3 * k + 1] = out[k].gy0; new_plan[3 * k + 2] = out[k].gy1; }
+    return 0;
+}
