@@ -553,6 +553,8 @@ extern "C" int hg_dispatch_particle(hg_ctx* c, float time, int should_rain) {
     if (rc) return rc;
     rc = hg_launch_particle_erode(c);
     if (rc) return rc;
+    // thermal x2 + smoothing: one fused kernel (TC/TD stay on chip), or the five 1:1 pass kernels on the PASSES schedule
+    if (c->schedule == HG_SCHEDULE_FUSED && !getenv("HG_DROPS_PASSES")) return hg_launch_fused_thermal_smooth_particle(c);
     return hg_launch_thermal_smooth_particle(c);
 }
 

@@ -245,7 +245,7 @@ __device__ __forceinline__ void cta_barrier() {
     asm volatile("barrier.sync 0;" ::: "memory");
 }
 
-template <int NT, int MINB, int RH, int RT>
+template <int NT, int MINB, int RH, int RT, bool DROPS>
 __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) float smb[];
     float* const sm = smb + FusedSmem<NT>::RINGS;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
             tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
         }                                                                                                            \
         mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
-        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         if (RH != RT) reg_inc<RT>();
 #define HG_ROW_T(FREEFLAG)                                                                                           \
     {                                                                                                                \
-        hg_fused_iter<NT, FREEFLAG, HGF_THERMAL>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
+        hg_fused_iter<NT, FREEFLAG, HGF_THERMAL, DROPS>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
@@ -435,7 +435,7 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     return HG_OK;
 }
 
-template <int NT, int MINB, int RH, int RT>
+template <int NT, int MINB, int RH, int RT, bool DROPS = false>
 static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     static_assert((RH + RT) / 2 * 2 * NT * MINB <= 65536 && RH % 8 == 0 && RT % 8 == 0, "register budget of the two warp groups");
     HgFusedK K = K0;
@@ -445,14 +445,14 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     constexpr size_t smem = FusedSmem<NT>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT, DROPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     alignas(64) CUtensorMap tmap;
     int rc = make_tmap(c, src_set, NT, &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
-    k_fused_ws<NT, MINB, RH, RT><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
+    k_fused_ws<NT, MINB, RH, RT, DROPS><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
@@ -474,10 +474,19 @@ static int align_sets(hg_ctx* c) {
     return HG_OK;
 }
 
-int hg_launch_fused_step(hg_ctx* c) {
+// drops = false: Erosion::dispatch_grid.  drops = true: the grid part of Erosion::dispatch_particle
+// (src/erosion.cpp:146-155: thermal x2 + smoothing with the momentum map) on the same kernel, the hydraulic warp
+// group only feeding (rock, dirt) to the thermal one; reads H and the momentum map, writes the other sets and H.a.
+static int launch_fused(hg_ctx* c, bool drops);
+int hg_launch_fused_step(hg_ctx* c) { return launch_fused(c, false); }
+int hg_launch_fused_thermal_smooth_particle(hg_ctx* c) { return launch_fused(c, true); }
+
+static int launch_fused(hg_ctx* c, bool drops) {
     if (c->g.plane_elems >= (size_t)1 << 32) { hg_set_error("slab too large for 32-bit plane offsets (%zu elements)", c->g.plane_elems); return HG_ERR_INVALID; }
-    int rca = align_sets(c);
-    if (rca) return rca;
+    if (!drops) {
+        int rca = align_sets(c);
+        if (rca) return rca;
+    }
     FusedArgs A;
     memset(&A, 0, sizeof(A));
     HgFusedK K;
@@ -494,7 +503,7 @@ int hg_launch_fused_step(hg_ctx* c) {
         A.slabs.n = 1; A.slabs.me = 0;
         A.slabs.arena[0] = c->arena; A.slabs.row0[0] = c->g.row0; A.slabs.rows[0] = c->g.rows;
     }
-    if (!c->far_list) {   // one entry per owned cell: correct even if every back-trace is far
+    if (!drops && !c->far_list) {   // one entry per owned cell: correct even if every back-trace is far
         HG_CUDA(cudaMalloc(&c->far_list, (size_t)c->g.rows * c->g.W * sizeof(unsigned)));
     }
     A.far_list = K.far_list = c->far_list;
@@ -503,12 +512,19 @@ int hg_launch_fused_step(hg_ctx* c) {
     A.far_total = c->d_counters;
     c->far_parity ^= 1;
     A.P = K.P = c->sp;
+    if (drops) {
+        // the nine-plane TMA box is read from H's set (only rock and dirt are used); F and S are not touched
+        for (int p = 0; p < HG_NPLANES; p++) { K.src[p] = hg_plane(c, c->ri[0], p); K.dst[p] = hg_plane(c, c->ri[0] ^ 1, p); }
+        for (int k = 0; k < 4; k++) { K.msrc[k] = hg_vel(c, k, 1); K.mdst[k] = hg_vel(c, k, 0); }
+        K.total_dst = hg_total(c, 0);
+    }
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
     // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA
     static const int nt_of[] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128};
     static const int res_of[] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4};
     static const int wpc_of[] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8};
     int v = c->tune_variant >= 0 && c->tune_variant < 10 ? c->tune_variant : 5;   // default: warp-specialised, 3 CTAs per SM
+    if (drops) v = 5;
     const int NT = nt_of[v];
     int nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
     // Rows per CTA.  A CTA runs seg + 17 row iterations (pipeline fill), about 8 of them of the
@@ -579,7 +595,7 @@ int hg_launch_fused_step(hg_ctx* c) {
     case 2: rc = launch_main<192, 2>(c, K, seg, c->ri[0]); break;
     case 3: rc = launch_main<224, 2>(c, K, seg, c->ri[0]); break;
     case 4: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
-    case 5: rc = launch_ws<128, 3, 72, 88>(c, K, seg, c->ri[0]); break;
+    case 5: rc = drops ? launch_ws<128, 3, 72, 88, true>(c, K, seg, c->ri[0]) : launch_ws<128, 3, 72, 88>(c, K, seg, c->ri[0]); break;
     case 6: rc = launch_ws<128, 2, 96, 128>(c, K, seg, c->ri[0]); break;
     case 7: rc = launch_ws<128, 3, 64, 96>(c, K, seg, c->ri[0]); break;
     case 8: rc = launch_ws<128, 4, 64, 64>(c, K, seg, c->ri[0]); break;
@@ -601,6 +617,10 @@ int hg_launch_fused_step(hg_ctx* c) {
         HG_CUDA(cudaEventRecord(c->ev_plan, c->plan_stream));
         c->plan_cur ^= 1;
         c->plan_valid = true;
+    }
+    if (drops) {
+        c->ri[0] ^= 1; c->ri[2] ^= 1;      // heightmap and momentum map were written into their other textures
+        return HG_OK;
     }
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);

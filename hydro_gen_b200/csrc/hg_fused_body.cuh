@@ -106,6 +106,10 @@ struct HgFusedK {
     // duration in cta_ns[b]; null = uniform segments of `seg` rows
     const HgPlanItem* plan;
     unsigned* cta_ns;
+    // droplet mode (DROPS): the momentum map (4 channels) and H.a planes read / written by the smoothing stage
+    const float* msrc[4];
+    float* mdst[4];
+    float* total_dst;
     HgStepParams P;
 };
 
@@ -135,7 +139,7 @@ HG_FN void hg_col_init(HgCol& c) {
 // thread; xin/owned: column inside the map / inside the strip proper; gy0, gy1: the CTA's
 // row segment; off: element offset of (row i, column x) inside a plane.
 // FREE: see the header.
-template <int NT, bool FREE, int GROUP = HGF_ALL>
+template <int NT, bool FREE, int GROUP = HGF_ALL, bool DROPS = false>
 HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
                          const int gy0, const int gy1, const int i, const unsigned off) {
     typedef HgRings<NT> R;
@@ -160,7 +164,26 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
 #define Q2(ring, k, d) (*reinterpret_cast<HgF2*>(B8(k) + (ring) + (d) * 8))
 #define Q2X(ring, k, d) (reinterpret_cast<const float*>(B8(k) + (ring) + (d) * 8)[0])   /* .x only: a 4-byte load */
 
-    if (GROUP != HGF_THERMAL) {
+    if (GROUP != HGF_THERMAL && DROPS) {
+    // ------------------------------------------------------------ droplet mode: no hydraulics
+    // Erosion::dispatch_particle (src/erosion.cpp:146-155) runs thermal x2 + smoothing on the heightmap the droplets
+    // left: this group only feeds the thermal group with (rock, dirt) of row i-1, as stage A does with (rockE, dirtE).
+    c.rk1 = c.rk2; c.dt1 = c.dt2;
+    {
+        const float* rw = raw + tid + 2;
+        constexpr int LD = HGF_RAW_LD(NT);
+        c.rk2 = rw[0 * LD]; c.dt2 = rw[1 * LD];
+    }
+    {
+        const int ya = i - 1;
+        if (FREE || (ya >= gy0 - 5 && ya < gy1 + 5)) {
+            const bool in = xin && (FREE || (ya >= 0 && ya < H));
+            HgF2 rd; rd.x = in ? c.rk1 : HG_OOB_HEIGHT; rd.y = in ? c.dt1 : HG_OOB_HEIGHT;
+            Q2(R::RD, 1, 0) = rd;
+        }
+    }
+    }
+    if (GROUP != HGF_THERMAL && !DROPS) {
     // ------------------------------------------------------------ L(i)
     c.rk0 = c.rk1; c.rk1 = c.rk2; c.dt0 = c.dt1; c.dt1 = c.dt2; c.at0 = c.at1; c.at1 = c.at2; c.w1 = c.w2;
     c.f0T = c.f1T; c.f1L = c.f2L; c.f1R = c.f2R; c.f1T = c.f2T; c.f1B = c.f2B; c.s1r = c.s2r; c.s1d = c.s2d;
@@ -345,6 +368,18 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 const unsigned idx = off - (unsigned)HGF_LAG_G * pitch;
                 K.dst[0][idx] = border ? rock : sr_;
                 K.dst[1][idx] = border ? dirt : sd_;
+                if (DROPS) {      // smoothing.glsl:77-101 with the momentum map bound: momentum relaxation, display-water decay, H.a
+                    float water = HGF_LDG(K.src[2] + idx);
+                    float mx = 0.0f, my = 0.0f, mz = 0.0f, mw = 0.0f;      // the border keeps its terrain; its momentum texel is defined as 0 (oracle: smooth_pass)
+                    if (!border && P.particle_count != 0) {
+                        mx = HGF_LDG(K.msrc[0] + idx); my = HGF_LDG(K.msrc[1] + idx); mz = HGF_LDG(K.msrc[2] + idx); mw = HGF_LDG(K.msrc[3] + idx);
+                        hg_smooth_momentum(P, mx, my, mz, mw, water);
+                    }
+                    K.dst[2][idx] = water;
+                    K.mdst[0][idx] = mx; K.mdst[1][idx] = my; K.mdst[2][idx] = mz; K.mdst[3][idx] = mw;
+                    // H.a: the border texel keeps what thermal_transport.glsl:63 left, an interior one gets smoothing.glsl:101: both (r + g) + b
+                    K.total_dst[idx] = (border ? rock : sr_) + (border ? dirt : sd_) + water;
+                }
             }
         }
     }

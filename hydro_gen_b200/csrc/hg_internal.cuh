@@ -150,6 +150,7 @@ static inline bool hg_total_live(const hg_ctx* c) { return c->aux && (c->schedul
 
 // implemented per file
 int hg_launch_passes_step(hg_ctx* c);
+int hg_launch_fused_thermal_smooth_particle(hg_ctx* c);
 int hg_launch_pass(hg_ctx* c, int pass);
 int hg_launch_fused_step(hg_ctx* c);
 int hg_launch_rain(hg_ctx* c, float time);
