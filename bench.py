@@ -10,7 +10,9 @@ thermal layers are live; a "step" is one iteration of the reference main loop
 (src/main.cpp:310-321: rain when due, then Erosion::dispatch_grid).  N>1: the same
 per-GPU work, weak scaling: a 4096-column map of 4096*N rows, one 4096-row slab per rank,
 one NVLink halo push + device-side flag wait per step (no collective on the data path).
-`value` is timed on the device with inputs resident in HBM; `e2e` runs every step through
+`value` is timed on the device with inputs resident in HBM (K steps between two CUDA events on
+the step stream, hg_run_profiled; the same run carries one event pair around every fused step
+kernel: roofline.kernel_ms is their average over the timed region); `e2e` runs every step through
 the C ABI from pinned HOST buffers (upload H,F,S in the reference's RGBA32F texture
 format, step, download H,F,S).  The working set (604 MB per plane set at 4096^2) exceeds
 the 126 MB L2, so no flush is needed between timed steps.
