@@ -181,3 +181,28 @@ def test_committed_golden_vectors_are_the_reference_shaders_outputs(name):
     ref.dispatch_grid(); ref.dispatch_grid()
     for k, f in (("H", "heightmap"), ("F", "flux"), ("V", "velocity"), ("S", "sediment")):
         assert_bit_equal(getattr(ref, f).read, cases[f"{name}/step3/out/{k}"], f"{name} step 3: {f}")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_parameters_match_the_reference_shaders(seed):
+    """randomised: small square maps (down to 8 x 8), random erosion / rain parameters and map seed, terrain from
+    heightmap.glsl, six main-loop iterations: oracle == reference shaders after every iteration"""
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.choice((8, 16, 24, 40, 64)))
+    orc = oracle.World(n, seed=float(rng.uniform(0.0, 5000.0)))
+    e = orc.erosion
+    e.Kc = float(rng.uniform(0.01, 2.0)); e.d_t = float(rng.uniform(0.001, 0.03)); e.G = float(rng.uniform(1.0, 20.0))
+    e.Ke = float(rng.uniform(0.0, 0.5)); e.ENERGY_KEPT = float(rng.uniform(0.5, 1.0)); e.Kconv = float(rng.uniform(0.0, 0.1))
+    for i in range(2):
+        e.Kalpha[i] = float(rng.uniform(0.1, 1.2)); e.Ks[i] = float(rng.uniform(0.001, 2.0)); e.Kd[i] = float(rng.uniform(0.001, 2.0))
+        e.Kspeed[i] = float(rng.uniform(0.1, 30.0))
+    orc.rain.period = int(rng.integers(1, 4)); orc.rain.amount = float(rng.uniform(0.001, 1.0)); orc.rain.drops = float(rng.uniform(0.005, 0.3))
+    ref = _ref_from(orc)
+    ref.gen_heightmap(); orc.gen_heightmap()
+    _compare(ref, orc, f"seed {seed}: init", ("heightmap",))
+    for s in range(1, 7):
+        t = float(np.float32(s) * np.float32(DT_TIME))
+        ref.step(s, t)
+        orc.step(t)
+        _compare(ref, orc, f"seed {seed} n={n} step {s}")
+    orc.close()
