@@ -127,6 +127,7 @@ struct HgCol {
     float p_old, q_old;                          // own (rock1, dirtE) of row i-9 (stage F)
     float so1_d1, so1_d2, T1_d1, T1_d2, T1_d3, B1_d1;
     float nR1_d1, nL1_d1, nRT1_d1, nRT1_d2, nLT1_d1, nLT1_d2;
+    float pf_w, pf_m0, pf_m1, pf_m2, pf_m3;      // droplet mode: water and momentum map of the NEXT smoothing row, fetched one iteration ahead
 };
 
 HG_FN void hg_col_init(HgCol& c) {
@@ -369,10 +370,10 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 K.dst[0][idx] = border ? rock : sr_;
                 K.dst[1][idx] = border ? dirt : sd_;
                 if (DROPS) {      // smoothing.glsl:77-101 with the momentum map bound: momentum relaxation, display-water decay, H.a
-                    float water = HGF_LDG(K.src[2] + idx);
+                    float water = c.pf_w;
                     float mx = 0.0f, my = 0.0f, mz = 0.0f, mw = 0.0f;      // the border keeps its terrain; its momentum texel is defined as 0 (oracle: smooth_pass)
                     if (!border && P.particle_count != 0) {
-                        mx = HGF_LDG(K.msrc[0] + idx); my = HGF_LDG(K.msrc[1] + idx); mz = HGF_LDG(K.msrc[2] + idx); mw = HGF_LDG(K.msrc[3] + idx);
+                        mx = c.pf_m0; my = c.pf_m1; mz = c.pf_m2; mw = c.pf_m3;
                         hg_smooth_momentum(P, mx, my, mz, mw, water);
                     }
                     K.dst[2][idx] = water;
@@ -380,6 +381,17 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                     // H.a: the border texel keeps what thermal_transport.glsl:63 left, an interior one gets smoothing.glsl:101: both (r + g) + b
                     K.total_dst[idx] = (border ? rock : sr_) + (border ? dirt : sd_) + water;
                 }
+            }
+        }
+        // These five planes are not staged through shared memory; fetching the next row's texels now keeps the
+        // global-load latency off the row's critical path (the loads were 2 stall cycles per issued instruction).
+        if (DROPS && owned) {
+            const int yn = yg + 1;
+            if ((FREE || yn >= gy0) && yn < gy1) {
+                const unsigned idn = off - (unsigned)(HGF_LAG_G - 1) * pitch;
+                c.pf_w = HGF_LDG(K.src[2] + idn);
+                c.pf_m0 = HGF_LDG(K.msrc[0] + idn); c.pf_m1 = HGF_LDG(K.msrc[1] + idn);
+                c.pf_m2 = HGF_LDG(K.msrc[2] + idn); c.pf_m3 = HGF_LDG(K.msrc[3] + idn);
             }
         }
     }
