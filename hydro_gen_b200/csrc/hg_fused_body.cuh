@@ -355,7 +355,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     // Smoothing reads only the G2 ring, so either group could run it.  The hydraulic group executes
     // 20 % fewer instructions per row than the thermal group, but moving G there was measured 6 %
     // slower (its instruction stream is the latency-heavy one: divisions, sqrt, the TMA wait).
-    if (GROUP == HGF_ALL || GROUP == HGF_SMOOTH_GROUP) {
+    // Droplet mode: the hydraulic group only feeds rows to the thermal group, so it takes the smoothing stage
+    // (and the momentum map) off the thermal group's hands.
+    if (GROUP == HGF_ALL || GROUP == (DROPS ? HGF_HYDRO : HGF_SMOOTH_GROUP)) {
         // own column of (rock1, dirt2): rows i-12 (y-1), i-11 (y), i-10 (y+1); stage F writes row i-9 meanwhile
         const int yg = i - HGF_LAG_G;
         if (FREE || (yg >= gy0 && yg < gy1)) {
