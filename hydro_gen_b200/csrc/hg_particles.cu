@@ -115,28 +115,48 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
     A.particles[id] = p;
 }
 
-// Add v to *addr for every active lane, combining lanes of the warp that target the same
-// address: the lowest such lane sums its peers' values in lane order and issues one red.
-// `active` marks lanes that take part (all 32 lanes must call).
-__device__ __forceinline__ void warp_red_add(float* addr, float v, bool active) {
-    unsigned long long key = active ? (unsigned long long)addr : ~0ull - (threadIdx.x & 31);
+struct ErodePlanes { float *rock, *dirt, *water, *mz, *mw; };
+
+// What one corner of one droplet adds to its texel (particle_erosion.glsl:61-75,94-98): deposits per layer
+// (only where the layer deposited), display water and the momentum accumulator.
+struct CornerAdd { float rock, dirt, water, mz, mw; bool has_rock, has_dirt; };
+
+// Apply the corner additions of all 32 lanes.  Lanes of the warp that hit the same texel are found with ONE
+// match per corner; the lowest such lane sums its peers' five values in lane order (a lane that has no deposit
+// for a layer contributes its 0.0f, which changes no sum) and issues one red per plane.  All 32 lanes must call.
+__device__ __forceinline__ void warp_corner_add(const ErodePlanes& A, size_t ti, const CornerAdd& v, bool act) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long key = act ? (unsigned long long)ti : ~0ull - lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(peers) - 1;
-    if (__popc(peers) == 1) {              // the common case: nobody else in the warp hits this texel
-        if (active) atomicAdd(addr, v);
+    unsigned rock_lanes = __ballot_sync(0xffffffffu, act && v.has_rock), dirt_lanes = __ballot_sync(0xffffffffu, act && v.has_dirt);
+    if (!act) return;
+    if (__popc(peers) == 1) {              // the common case on a sparse map: nobody else in the warp hits this texel
+        if (v.has_dirt) atomicAdd(A.dirt + ti, v.dirt);
+        if (v.has_rock) atomicAdd(A.rock + ti, v.rock);
+        atomicAdd(A.water + ti, v.water);
+        atomicAdd(A.mz + ti, v.mz);
+        atomicAdd(A.mw + ti, v.mw);
         return;
     }
     // peers > 1 only occurs among active lanes (inactive keys are unique)
-    float sum = 0.0f;
+    float s_rock = 0.0f, s_dirt = 0.0f, s_water = 0.0f, s_mz = 0.0f, s_mw = 0.0f;
     unsigned rest = peers;
     while (rest) {
         int src = __ffs(rest) - 1;
         rest &= rest - 1;
-        float pv = __shfl_sync(peers, v, src);
-        sum += pv;
+        s_rock += __shfl_sync(peers, v.rock, src);
+        s_dirt += __shfl_sync(peers, v.dirt, src);
+        s_water += __shfl_sync(peers, v.water, src);
+        s_mz += __shfl_sync(peers, v.mz, src);
+        s_mw += __shfl_sync(peers, v.mw, src);
     }
-    if (lane == leader) atomicAdd(addr, sum);
+    if (lane == __ffs(peers) - 1) {
+        if (dirt_lanes & peers) atomicAdd(A.dirt + ti, s_dirt);
+        if (rock_lanes & peers) atomicAdd(A.rock + ti, s_rock);
+        atomicAdd(A.water + ti, s_water);
+        atomicAdd(A.mz + ti, s_mz);
+        atomicAdd(A.mw + ti, s_mw);
+    }
 }
 
 // terr -= eroded with the exhausted-layer clamp of particle_erosion.glsl:53-59, as one
@@ -156,7 +176,7 @@ __device__ __forceinline__ float erode_clamped(float* addr, float eroded, float*
     return __uint_as_float(assumed);
 }
 
-struct ErodeArgs { float *rock, *dirt, *water, *mz, *mw; hg_particle* particles; };
+struct ErodeArgs : ErodePlanes { hg_particle* particles; };
 
 // particle_erosion.glsl:101-128 + erode_layers :22-85
 __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, ErodeArgs A, uint32_t count) {
@@ -165,7 +185,7 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
     hg_particle part = {};
     if (live) part = A.particles[id];
     live = live && part.iters != 0;
-    // all lanes stay in the loop: warp_red_add is warp-collective
+    // all lanes stay in the loop: warp_corner_add is warp-collective
     int bx = 0, by = 0;
     float offx = 0.0f, offy = 0.0f, old_sed[2] = {0.0f, 0.0f};
     if (live) {
@@ -221,11 +241,12 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
             part.sediment[1] += conv;
             part.sediment[0] -= conv;
         }
-        warp_red_add(A.dirt + ti, dep[1], act && has_dep[1]);
-        warp_red_add(A.rock + ti, dep[0], act && has_dep[0]);
-        warp_red_add(A.water + ti, 1e-5f * part.volume * multipl, act);
-        warp_red_add(A.mz + ti, part.volume * part.velocity[0] * multipl, act);
-        warp_red_add(A.mw + ti, part.volume * part.velocity[1] * multipl, act);
+        CornerAdd v;
+        v.rock = dep[0]; v.dirt = dep[1]; v.has_rock = has_dep[0]; v.has_dirt = has_dep[1];
+        v.water = 1e-5f * part.volume * multipl;
+        v.mz = part.volume * part.velocity[0] * multipl;
+        v.mw = part.volume * part.velocity[1] * multipl;
+        warp_corner_add(A, ti, v, act);
     }
     if (live) A.particles[id] = part;
 }
@@ -247,7 +268,9 @@ int hg_launch_particle_erode(hg_ctx* c) {
     uint32_t count = (c->particle_count / 64u) * 64u;
     if (!count) return HG_OK;
     // in place on the READ images of heightmap and momentum map (erosion.cpp:141-143)
-    ErodeArgs A{hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1), hg_vel(c, 2, 1), hg_vel(c, 3, 1), c->particles};
+    ErodeArgs A;
+    A.rock = hg_cur(c, PL_ROCK, 1); A.dirt = hg_cur(c, PL_DIRT, 1); A.water = hg_cur(c, PL_WATER, 1);
+    A.mz = hg_vel(c, 2, 1); A.mw = hg_vel(c, 3, 1); A.particles = c->particles;
     k_particle_erode<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
