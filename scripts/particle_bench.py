@@ -16,6 +16,6 @@ for name, hmap in (("4a faithful (hmap 1024)", 1024), ("4b corrected (hmap 8192)
     ctx.timer_start()
     ctx.run(steps, 21 * 0.015, 0.015, True)
     ms = ctx.timer_stop() / steps
-    print(f"{name}: {ms:.3f} ms/step, {COUNT / ms / 1e3:.1f} Mdroplet-steps/s, {N * N / ms / 1e6:.2f} Gcell-steps/s of the grid part "
+    print(f"{name}: {ms:.3f} ms/step, {COUNT / ms / 1e3:.1f} Mdroplet-steps/s ({20 * COUNT / ms / 1e6:.1f} G atomic updates/s), {N * N / ms / 1e6:.2f} Gcell-steps/s of the grid part "
           f"(thermal x2 + smoothing + momentum decay), launches/step {ctx.launch_count / (steps + 20):.1f}", flush=True)
     ctx.close()

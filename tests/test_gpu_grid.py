@@ -208,6 +208,32 @@ def test_steep_terrain_thermal_marks(built):
     ctx.close(); ref.close()
 
 
+def test_settings_hot_reload_between_steps(built, wet256):
+    """Erosion_settings / Rain_settings::push_data between steps (rendering.cpp:200-201,255-257: the UI pushes the
+    whole struct while the simulation runs): new parameters apply from the next dispatch on, with no re-creation —
+    including the ones baked into the step parameters (d_t, Kalpha -> talus tangents) and the rain period."""
+    ctx = Context(256)
+    copy_state(wet256, ctx)
+    ctx.set_map(_lib.MapSettingsData.from_buffer_copy(bytes(wet256.map)))
+    ctx.steps = wet256.steps
+    ref = _clone_oracle(wet256, 256)
+    t = np.float32((wet256.steps + 1) * DT_TIME)
+    for d_t, kc, kalpha, period, amount in ((0.001, 0.2, (1.3, 0.6), 16, 0.01), (0.004, 0.35, (0.8, 0.4), 3, 0.02),
+                                            (0.0005, 0.1, (1.0, 0.7), 5, 0.005)):
+        e = ref.erosion
+        e.d_t, e.Kc, e.Kalpha[0], e.Kalpha[1] = d_t, kc, kalpha[0], kalpha[1]
+        ref.rain.period, ref.rain.amount = period, amount
+        ctx.set_erosion(_lib.ErosionData.from_buffer_copy(bytes(ref.erosion)))
+        ctx.set_rain(_lib.RainData.from_buffer_copy(bytes(ref.rain)))
+        for _ in range(7):
+            ctx.run(1, float(t), DT_TIME, True)
+            ref.step(t)
+            t = np.float32(t + np.float32(DT_TIME))
+        _compare(ctx, ref, ("heightmap", "flux", "sediment"), f"after push_data(d_t={d_t}, period={period})")
+    assert ctx.steps == ref.steps
+    ctx.close(); ref.close()
+
+
 @pytest.mark.parametrize("kspeed", [1e-30, 3e8])
 def test_thermal_outflow_generic_division(built, kspeed):
     """Kspeed so small (or so large) that S = d_t*Kspeed*sharpness*H/2 leaves the range in which the
