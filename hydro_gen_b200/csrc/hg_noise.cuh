@@ -44,9 +44,11 @@ HG_FN float hg_simplex(float vx, float vy) {
     x1y -= i1y;
     ix = hg_mod289(ix);
     iy = hg_mod289(iy);
-    float p0 = hg_permute(hg_permute(iy + 0.0f) + ix + 0.0f);
-    float p1 = hg_permute(hg_permute(iy + i1y) + ix + i1x);
-    float p2 = hg_permute(hg_permute(iy + 1.0f) + ix + 1.0f);
+    // i1y is 0 or 1, so the inner permute of the middle corner is one of the other two (same expression, same bits)
+    const float in0 = hg_permute(iy + 0.0f), in2 = hg_permute(iy + 1.0f);
+    float p0 = hg_permute(in0 + ix + 0.0f);
+    float p1 = hg_permute(((x0x > x0y) ? in0 : in2) + ix + i1x);
+    float p2 = hg_permute(in2 + ix + 1.0f);
     float m0 = hg_max(0.5f - (x0x * x0x + x0y * x0y), 0.0f);
     float m1 = hg_max(0.5f - (x1x * x1x + x1y * x1y), 0.0f);
     float m2 = hg_max(0.5f - (x2x * x2x + x2y * x2y), 0.0f);
