@@ -106,6 +106,7 @@ SYMBOLS = {
     "hg_slab_connect_local": (_i, [_vp, C.POINTER(_vp), _i, _i]),
     "hg_slab_set_ghost": (_i, [_vp, _i, _i, _vp]),
     "hg_slab_errors": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "hg_slab_refresh_halo": (_i, [_vp]),
     "hg_register_gl": (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "hg_publish_gl": (_i, [_vp, _i]),
 }

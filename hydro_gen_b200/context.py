@@ -196,6 +196,10 @@ class Context:
     def slab_errors(self):
         v = C.c_uint64(); check(self.L.hg_slab_errors(self.h, C.byref(v))); return v.value
 
+    def refresh_halo(self):
+        """hg_slab_refresh_halo: collective re-fill of the ghost rows after uploads on a connected slab"""
+        check(self.L.hg_slab_refresh_halo(self.h))
+
     # ---- checkpoint (hg_checkpoint.cu; hydro_gen_b200.checkpoint reads the files without a GPU)
     def save_checkpoint(self, path):
         check(self.L.hg_checkpoint_save(self.h, str(path).encode()))

@@ -9,7 +9,8 @@
 //
 // The binary header is what hg_checkpoint_load reads; the JSON block repeats it for people and
 // tools (hydro_gen_b200/checkpoint.py reads both).  A slab saves its own rows; load requires a
-// context of the same geometry and mode.
+// context of the same geometry and mode, and on a connected slab ends with a collective halo refresh
+// (hg_slab_refresh_halo), so every rank loads its file at the same point.
 #include <cstddef>
 #include <cstdio>
 #include <string>
@@ -93,22 +94,31 @@ extern "C" int hg_checkpoint_save(hg_ctx* c, const char* path) {
     h.payload_bytes = h.n_fields * field_bytes + part_bytes;
     const std::string json = make_json(h);
     h.json_bytes = (uint32_t)json.size();
+    // written to a temporary file beside the target and renamed once complete and flushed, so a crash or a
+    // full disk never leaves a half-written file under the checkpoint's name
+    const std::string tmp = std::string(path) + ".tmp";
     File out;
-    out.f = fopen(path, "wb");
-    if (!out.f) { hg_set_error("cannot open %s for writing", path); return HG_ERR_INVALID; }
-    if (fwrite(&h, sizeof(h), 1, out.f) != 1 || fwrite(json.data(), 1, json.size(), out.f) != json.size()) { hg_set_error("short write to %s", path); return HG_ERR_STATE; }
-    float* host = static_cast<float*>(hg_host_alloc(field_bytes > part_bytes ? field_bytes : part_bytes));
-    if (!host) return HG_ERR_CUDA;
+    out.f = fopen(tmp.c_str(), "wb");
+    if (!out.f) { hg_set_error("cannot open %s for writing", tmp.c_str()); return HG_ERR_INVALID; }
     int rc = HG_OK;
+    if (fwrite(&h, sizeof(h), 1, out.f) != 1 || fwrite(json.data(), 1, json.size(), out.f) != json.size()) { hg_set_error("short write to %s", tmp.c_str()); rc = HG_ERR_STATE; }
+    float* host = rc == HG_OK ? static_cast<float*>(hg_host_alloc(field_bytes > part_bytes ? field_bytes : part_bytes)) : nullptr;
+    if (rc == HG_OK && !host) rc = HG_ERR_CUDA;
     for (uint32_t k = 0; k < h.n_fields && rc == HG_OK; k++) {
         rc = hg_download(c, h.field_ids[k], host);
-        if (rc == HG_OK && fwrite(host, 1, field_bytes, out.f) != field_bytes) { hg_set_error("short write to %s", path); rc = HG_ERR_STATE; }
+        if (rc == HG_OK && fwrite(host, 1, field_bytes, out.f) != field_bytes) { hg_set_error("short write to %s", tmp.c_str()); rc = HG_ERR_STATE; }
     }
     if (rc == HG_OK && part_bytes) {
         rc = hg_download_particles(c, reinterpret_cast<hg_particle*>(host), c->particle_count);
-        if (rc == HG_OK && fwrite(host, 1, part_bytes, out.f) != part_bytes) { hg_set_error("short write to %s", path); rc = HG_ERR_STATE; }
+        if (rc == HG_OK && fwrite(host, 1, part_bytes, out.f) != part_bytes) { hg_set_error("short write to %s", tmp.c_str()); rc = HG_ERR_STATE; }
     }
-    hg_host_free(host);
+    if (host) hg_host_free(host);
+    if (rc == HG_OK && fflush(out.f) != 0) { hg_set_error("flush of %s failed", tmp.c_str()); rc = HG_ERR_STATE; }
+    FILE* f = out.f;
+    out.f = nullptr;
+    if (fclose(f) != 0 && rc == HG_OK) { hg_set_error("close of %s failed", tmp.c_str()); rc = HG_ERR_STATE; }
+    if (rc == HG_OK && rename(tmp.c_str(), path) != 0) { hg_set_error("cannot rename %s to %s", tmp.c_str(), path); rc = HG_ERR_STATE; }
+    if (rc != HG_OK) remove(tmp.c_str());
     return rc;
 }
 
@@ -131,9 +141,11 @@ extern "C" int hg_checkpoint_load(hg_ctx* c, const char* path) {
     }
     const size_t field_bytes = (size_t)c->g.rows * c->g.W * 4 * sizeof(float);
     const size_t part_bytes = c->erosion_type == HG_PARTICLES ? (size_t)c->particle_count * sizeof(hg_particle) : 0;
-    if (h.payload_bytes != h.n_fields * field_bytes + part_bytes || fseek(in.f, (long)h.json_bytes, SEEK_CUR) != 0) {
-        hg_set_error("%s: payload size does not match its header", path); return HG_ERR_INVALID;
-    }
+    if (h.payload_bytes != h.n_fields * field_bytes + part_bytes) { hg_set_error("%s: payload size does not match its header", path); return HG_ERR_INVALID; }
+    // the whole payload must be there BEFORE the context is touched: a truncated file leaves it as it was
+    const long payload_at = (long)(sizeof(h) + h.json_bytes);
+    if (fseek(in.f, 0, SEEK_END) != 0 || (uint64_t)ftell(in.f) < (uint64_t)payload_at + h.payload_bytes) { hg_set_error("%s is truncated", path); return HG_ERR_INVALID; }
+    if (fseek(in.f, payload_at, SEEK_SET) != 0) { hg_set_error("cannot seek in %s", path); return HG_ERR_INVALID; }
     float* host = static_cast<float*>(hg_host_alloc(field_bytes > part_bytes ? field_bytes : part_bytes));
     if (!host) return HG_ERR_CUDA;
     int rc = hg_set_erosion(c, &h.erosion);
@@ -149,5 +161,8 @@ extern "C" int hg_checkpoint_load(hg_ctx* c, const char* path) {
     }
     if (rc == HG_OK) c->erosion_steps = h.erosion_steps;
     hg_host_free(host);
+    // A connected slab also needs its neighbours' edge rows in its ghost rows (the file holds owned rows only):
+    // collective push + wait, every rank of the slab table loads its own file.
+    if (rc == HG_OK) rc = hg_slab_refresh_halo(c);
     return rc;
 }

@@ -38,6 +38,7 @@ static void free_ctx(hg_ctx* c) {
     if (c->ev_comp) cudaEventDestroy(c->ev_comp);
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
     if (c->ev_down) cudaEventDestroy(c->ev_down);
+    if (c->h_sticky) cudaFreeHost(c->h_sticky);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->far_list) cudaFree(c->far_list);
     if (c->plan_stream) { cudaStreamSynchronize(c->plan_stream); cudaStreamDestroy(c->plan_stream); }
@@ -457,7 +458,7 @@ extern "C" int hg_sync(hg_ctx* c) {
     HG_CUDA(cudaStreamSynchronize(c->stream));
     if (c->up_stream) HG_CUDA(cudaStreamSynchronize(c->up_stream));
     if (c->down_stream) HG_CUDA(cudaStreamSynchronize(c->down_stream));
-    return HG_OK;
+    return hg_slab_check_sticky(c);
 }
 extern "C" int hg_set_stream(hg_ctx* c, void* s) {
     HG_CHECK_CTX(c);
@@ -494,14 +495,23 @@ extern "C" int hg_gen_heightmap(hg_ctx* c) { HG_CHECK_CTX(c); return hg_launch_h
 extern "C" int hg_dispatch_grid_rain(hg_ctx* c, float time) {
     HG_CHECK_CTX(c);
     if (c->erosion_type != HG_GRID) { hg_set_error("dispatch_grid_rain on a particle context (prog.grid is null in the reference)"); return HG_ERR_STATE; }
-    return hg_launch_rain(c, time);
+    int rc = hg_slab_check_sticky(c);
+    if (rc) return rc;
+    rc = hg_launch_rain(c, time);
+    if (rc) return rc;
+    // On the FUSED schedule rain is added in place to the planes the next step reads, ghost rows included (pointwise
+    // in the global coordinate, so no push is needed).  A peer's far fetch of that step reads this rank's water
+    // through its peer pointer: an all-rank generation makes sure every rank's rain has landed first.
+    return hg_slab_barrier(c, false);
 }
 
 extern "C" int hg_dispatch_grid(hg_ctx* c) {
     HG_CHECK_CTX(c);
     if (c->erosion_type != HG_GRID) { hg_set_error("dispatch_grid on a particle context"); return HG_ERR_STATE; }
     if (c->schedule == HG_SCHEDULE_PASSES) return hg_launch_passes_step(c);
-    int rc = hg_launch_fused_step(c);
+    int rc = hg_slab_check_sticky(c);
+    if (rc) return rc;
+    rc = hg_launch_fused_step(c);
     if (rc) return rc;
     return hg_slab_exchange(c);
 }

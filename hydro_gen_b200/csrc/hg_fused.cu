@@ -31,6 +31,7 @@
 #define HG_FREE_UNROLL 1
 #endif
 constexpr int kFreeUnroll = HG_FREE_UNROLL;
+constexpr int HG_MAX_DEVICES = 64;
 
 namespace {
 
@@ -420,10 +421,10 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     K.seg = seg;
     int nseg = (c->g.rows + seg - 1) / seg;
     constexpr size_t smem = FusedSmem<NT>::BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[HG_MAX_DEVICES] = {};      // the attribute is per device (one process may drive several GPUs)
+    if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
         HG_CUDA(cudaFuncSetAttribute(k_fused_step<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
     int rc = make_tmap(c, src_set, NT, &tmap);
@@ -443,10 +444,10 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     K.seg = seg;
     int nseg = (c->g.rows + seg - 1) / seg;
     constexpr size_t smem = FusedSmem<NT>::BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[HG_MAX_DEVICES] = {};
+    if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
         HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT, DROPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
     int rc = make_tmap(c, src_set, NT, &tmap);

@@ -102,6 +102,9 @@ struct hg_ctx {
     bool slab_ipc[HG_MAX_SLABS];
     uint32_t step_flag;        // halo generation counter
     bool peers_connected;
+    unsigned* h_sticky;        // mapped pinned word raised by a timed-out halo wait (hg_slab.cu); d_sticky = its device alias
+    unsigned* d_sticky;
+    unsigned long long halo_timeout_ns;
 };
 
 void hg_set_error(const char* fmt, ...);
@@ -159,4 +162,6 @@ int hg_launch_particle_move(hg_ctx* c, float time, int should_rain);
 int hg_launch_particle_erode(hg_ctx* c);
 int hg_launch_thermal_smooth_particle(hg_ctx* c);
 int hg_slab_exchange(hg_ctx* c);     // push edge rows to neighbours + wait (no-op without peers)
+int hg_slab_barrier(hg_ctx* c, bool push);   // generation signal + all-rank wait, with or without the edge-row push
+int hg_slab_check_sticky(hg_ctx* c); // HG_ERR_STATE once a halo wait has timed out on this context
 void hg_slab_disconnect(hg_ctx* c);

@@ -16,6 +16,7 @@
 // PRE-step planes of any rank through its peer pointer.  That read is only safe while no
 // rank is a step ahead (it would be overwriting those planes) or behind (still writing
 // them); the all-rank flag wait is that guarantee.
+#include <stdlib.h>
 #include "hg_internal.cuh"
 
 namespace {
@@ -61,17 +62,32 @@ __global__ void __launch_bounds__(256) k_halo_push_signal(PushArgs A) {
     }
 }
 
-// bounded spin until every rank's word in MY flag page reached `gen`; on timeout it records
-// an error instead of hanging the GPU
-__global__ void k_halo_wait(FlagArgs F, unsigned gen, unsigned long long* err) {
+// Bounded spin until every rank's word in MY flag page reached `gen`.  On timeout (limit_ns of wall time on the
+// device's global timer; HG_HALO_TIMEOUT_S, default 60 s) it counts an error and raises the context's STICKY error
+// word in mapped host memory instead of hanging the GPU: the host sees it without a synchronisation and every
+// later hg_run / hg_dispatch_grid / hg_sync on the context fails with HG_ERR_STATE (the ghost rows are stale).
+__global__ void k_halo_wait(FlagArgs F, unsigned gen, unsigned long long limit_ns, unsigned long long* err, volatile unsigned* sticky) {
     if ((int)threadIdx.x >= F.n || !F.flag[threadIdx.x]) return;
     const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(F.flag[threadIdx.x]);
-    long long t0 = clock64();
-    const long long limit = 6000000000LL;   // ~3 s
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while ((int)(*f - gen) < 0) {
-        if (clock64() - t0 > limit) { atomicAdd(err, 1ull); return; }
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > limit_ns) {
+            atomicAdd(err, 1ull);
+            if (sticky) { *sticky = gen; __threadfence_system(); }
+            return;
+        }
         __nanosleep(100);
     }
+    __threadfence_system();
+}
+
+// generation signal without a push (hg_slab_barrier(c, false))
+__global__ void k_halo_signal(FlagArgs sig, unsigned gen) {
+    __threadfence_system();
+    if ((int)threadIdx.x < sig.n && sig.flag[threadIdx.x]) *reinterpret_cast<volatile unsigned*>(sig.flag[threadIdx.x]) = gen;
     __threadfence_system();
 }
 
@@ -183,10 +199,37 @@ extern "C" int hg_slab_errors(hg_ctx* c, uint64_t* count) {
     return HG_OK;
 }
 
-// After a fused step: push my new edge rows to both neighbours, publish the generation on
-// every rank, then make this stream wait until every rank has published it.
-int hg_slab_exchange(hg_ctx* c) {
+// The sticky error word of k_halo_wait: mapped pinned host memory, so the host reads it without synchronising.
+static int ensure_sticky(hg_ctx* c) {
+    if (c->h_sticky) return HG_OK;
+    HG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_sticky), sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_sticky = 0u;
+    HG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_sticky), c->h_sticky, 0));
+    double s = 60.0;
+    if (const char* e = getenv("HG_HALO_TIMEOUT_S")) { double v = atof(e); if (v > 0.0) s = v; }
+    c->halo_timeout_ns = (unsigned long long)(s * 1e9);
+    return HG_OK;
+}
+
+int hg_slab_check_sticky(hg_ctx* c) {
+    if (c->h_sticky && *reinterpret_cast<volatile unsigned*>(c->h_sticky) != 0u) {
+        hg_set_error("a halo wait timed out at exchange generation %u (a rank fell more than %.0f s behind or died): the ghost rows of this slab are stale",
+                     *c->h_sticky, (double)c->halo_timeout_ns * 1e-9);
+        return HG_ERR_STATE;
+    }
+    return HG_OK;
+}
+
+int hg_slab_exchange(hg_ctx* c) { return hg_slab_barrier(c, true); }
+
+// After a fused step (push = true): push my new edge rows to both neighbours, publish the generation on
+// every rank, then make this stream wait until every rank has published it.  push = false: only the
+// generation signal + wait, an all-rank barrier on the device (after an in-place rain: a peer's far fetch of
+// the next step must not read this rank's water before the rain has been added).
+int hg_slab_barrier(hg_ctx* c, bool push) {
     if (!c->peers_connected) return HG_OK;
+    int rcs = ensure_sticky(c);
+    if (rcs) return rcs;
     const HgSlabTable& T = c->slabs;
     c->step_flag++;
     const unsigned gen = c->step_flag;
@@ -218,11 +261,23 @@ int hg_slab_exchange(hg_ctx* c) {
     }
     A.gen = gen;
     A.done = reinterpret_cast<unsigned*>(c->d_counters + 10);
-    size_t blocks = (A.n / 4 + 255) / 256;
-    dim3 grid((unsigned)(blocks < 16 ? blocks : 16), HG_NPLANES, 2);
-    k_halo_push_signal<<<grid, 256, 0, c->stream>>>(A);
+    if (push) {
+        size_t blocks = (A.n / 4 + 255) / 256;
+        dim3 grid((unsigned)(blocks < 16 ? blocks : 16), HG_NPLANES, 2);
+        k_halo_push_signal<<<grid, 256, 0, c->stream>>>(A);
+    } else {
+        k_halo_signal<<<1, 32, 0, c->stream>>>(A.sig, gen);
+    }
     HG_LAUNCH_CHECK(c);
-    k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, gen, c->d_counters + 1);
+    k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, gen, c->halo_timeout_ns, c->d_counters + 1, c->d_sticky);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
+}
+
+// Ghost rows after the owned rows were replaced from outside (hg_upload, hg_checkpoint_load): every rank pushes
+// its edge rows to its neighbours and waits for theirs.  Collective: every rank of the slab table must call it
+// (hg_checkpoint_load does; after plain uploads the caller does), in the same order relative to its steps.
+extern "C" int hg_slab_refresh_halo(hg_ctx* c) {
+    HG_CHECK_CTX(c);
+    return hg_slab_barrier(c, true);
 }

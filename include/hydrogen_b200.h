@@ -3,7 +3,7 @@
  * The reference has no FFI: its erosion path is five C++ free functions and two
  * structs behind an OpenGL context.  Each entry point below
  * names the reference symbol it replaces.  A header-only C++ shim
- * (host/erosion_shim.hpp) re-creates `namespace Erosion` / `State::World` with
+ * (host/hydrogen_erosion.hpp) re-creates `namespace Erosion` / `State::World` with
  * the reference signatures on top of this ABI; INTEGRATION.md shows the patch
  * to src/main.cpp.
  *
@@ -193,8 +193,16 @@ int hg_slab_connect_local(hg_ctx* ctx, hg_ctx* const* all, int n, int my_index);
 /* Fill the ghost rows from host arrays instead (testing): rows_rgba32f holds
  * HG_HALO_ROWS rows of the field below (side 0) or above (side 1) the slab. */
 int hg_slab_set_ghost(hg_ctx* ctx, int field, int side, const float* rows_rgba32f);
-/* Halo waits that timed out + far fetches that found no owner, since creation. Blocking. */
+/* Halo waits that timed out + far fetches that found no owner, since creation. Blocking.
+ * A timed-out wait (a rank more than HG_HALO_TIMEOUT_S seconds behind, default 60) is also STICKY:
+ * from then on hg_run, hg_dispatch_grid, hg_dispatch_grid_rain and hg_sync on this context return
+ * HG_ERR_STATE, because its ghost rows are stale. */
 int hg_slab_errors(hg_ctx* ctx, uint64_t* count);
+/* Re-fill the ghost rows after the owned rows were replaced from outside (hg_upload on a connected
+ * slab): every rank pushes its edge rows and waits for its neighbours'.  Collective over the slab
+ * table: every rank calls it once, at the same point of its schedule.  hg_checkpoint_load calls it
+ * itself on a connected slab (so loading is collective too).  No-op on an unconnected context. */
+int hg_slab_refresh_halo(hg_ctx* ctx);
 
 /* ---- optional CUDA-GL interop with the reference renderer (src/rendering.cpp:104-105).
  * Compiled only with -DHG_WITH_GL (no GL in the build image); otherwise HG_ERR_STATE. ---- */

@@ -67,6 +67,8 @@ if os.path.exists(rep):
         f.write(f"{'dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch)':95s} {dr + dw:16.0f} byte\n")
     js = {"kernel": row[hdr.index("Kernel Name")], "duration_us": g("gpu__time_duration.sum"), "dram_bytes_per_launch": dr + dw,
           "dram_read_bytes": dr, "dram_write_bytes": dw, "inst_executed": g("inst_executed"),
-          "registers": g("launch__registers_per_thread"), "ipc_active": g("sm__inst_executed.avg.per_cycle_active")}
+          "registers": g("launch__registers_per_thread"), "ipc_active": g("sm__inst_executed.avg.per_cycle_active"),
+          # map size of the captured launch (bench.py reports roofline.traffic only for a run of the same size)
+          "cells_per_launch": int(os.environ.get("NCU_CELLS", 4096 * 4096))}
     json.dump(js, open(os.path.join(ROOT, "profiles", f"{tag}_{name}.json"), "w"), indent=1)
     print(open(os.path.join(ROOT, "profiles", f"{tag}_{name}.txt")).read())

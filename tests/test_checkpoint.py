@@ -133,3 +133,66 @@ def test_particle_checkpoint_roundtrip(built, tmp_path):
     assert_bit_equal(b.download(_lib.FIELD_VELOCITY), a.download(_lib.FIELD_VELOCITY), "momentum map")
     assert np.array_equal(np.asarray(b.download_particles()).view(np.uint8), np.asarray(a.download_particles()).view(np.uint8))
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_slab_checkpoint_resume_matches_whole_map(built, tmp_path):
+    """Three connected slabs save their own rows and are resumed into three NEW connected slabs: the load ends with
+    the collective halo refresh (hg_slab_refresh_halo), so the first fused step after the resume reads the neighbours'
+    edge rows, and the resumed slabs keep reproducing the whole-map run bit for bit, rain steps included.
+    A truncated file is refused before it touches the context."""
+    from hydro_gen_b200 import Context
+    n, cuts = 128, [0, 40, 88, 128]
+
+    def make_slabs():
+        ss = [Context(n, n, row0=cuts[i], rows=cuts[i + 1] - cuts[i]) for i in range(3)]
+        for i, s in enumerate(ss):
+            s.connect_local(ss, i)
+        return ss
+
+    def setup(c):
+        m = c.get_map(); m.seed = SEED; c.set_map(m)
+        r = c.get_rain(); r.period = 4; c.set_rain(r)
+        c.gen_heightmap()
+
+    whole = Context(n)
+    setup(whole)
+    slabs = make_slabs()
+    for s in slabs:
+        setup(s)
+    for k in range(10):
+        t = (k + 1) * DT_TIME
+        whole.run(1, t, DT_TIME, True)
+        for s in slabs:
+            s.run(1, t, DT_TIME, True)
+    paths = [tmp_path / f"slab{i}.hgck" for i in range(3)]
+    for s, p in zip(slabs, paths):
+        s.save_checkpoint(p)
+        s.close()
+    resumed = make_slabs()          # fresh contexts: zero ghost rows, default settings
+    for s, p in zip(resumed, paths):
+        s.load_checkpoint(p)
+    for k in range(10, 19):         # crosses rain steps 12 and 16
+        t = (k + 1) * DT_TIME
+        whole.run(1, t, DT_TIME, True)
+        for s in resumed:
+            s.run(1, t, DT_TIME, True)
+    for s in resumed:
+        s.sync()
+        assert s.slab_errors() == 0
+    for fid, name in ((_lib.FIELD_HEIGHTMAP, "heightmap"), (_lib.FIELD_FLUX, "flux"), (_lib.FIELD_SEDIMENT, "sediment")):
+        got = np.concatenate([s.download(fid) for s in resumed], axis=0)
+        assert_bit_equal(got, whole.download(fid), f"resumed slabs vs whole map: {name}")
+    # truncated file: refused, and the context keeps its state and settings
+    data = paths[0].read_bytes()
+    (tmp_path / "cut.hgck").write_bytes(data[: len(data) - 1000])
+    before = resumed[0].download(_lib.FIELD_HEIGHTMAP)
+    steps = resumed[0].steps
+    with pytest.raises(_lib.HydrogenError):
+        resumed[0].load_checkpoint(tmp_path / "cut.hgck")
+    assert resumed[0].steps == steps
+    assert_bit_equal(resumed[0].download(_lib.FIELD_HEIGHTMAP), before, "state after a refused load")
+    assert not (tmp_path / "slab0.hgck.tmp").exists()
+    for s in resumed:
+        s.close()
+    whole.close()

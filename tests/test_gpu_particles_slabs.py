@@ -72,6 +72,15 @@ def test_particle_full_step_statistical(built):
     gp, wp = ctx.download_particles(), ref.particles()
     assert np.array_equal(gp["iters"], wp["iters"]) and np.array_equal(gp["to_kill"], wp["to_kill"])
     np.testing.assert_allclose(gp["position"], wp["position"], rtol=0, atol=1e-3)
+    # Mass accounting.  The algorithm itself does not conserve mass (the droplet keeps the sediment
+    # of its last corner only), so the invariant is against the oracle: the totals of every map channel and of the
+    # sediment the droplets carry are sums of the same terms in another order and must agree to reassociation noise.
+    for ch, name in enumerate(("rock", "dirt", "water")):
+        a, b = got[..., ch].sum(dtype=np.float64), want[..., ch].sum(dtype=np.float64)
+        assert abs(a - b) <= 1e-6 * abs(b) + 1e-6, f"map total of {name}: {a} vs {b}"
+    for i in range(2):
+        a, b = gp["sediment"][:, i].sum(dtype=np.float64), wp["sediment"][:, i].sum(dtype=np.float64)
+        assert abs(a - b) <= 1e-4 * abs(b) + 1e-6, f"carried sediment of layer {i}: {a} vs {b}"
     ctx.close(); ref.close()
 
 
