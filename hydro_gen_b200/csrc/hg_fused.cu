@@ -484,6 +484,10 @@ int hg_launch_fused_thermal_smooth_particle(hg_ctx* c) { return launch_fused(c, 
 
 static int launch_fused(hg_ctx* c, bool drops) {
     if (c->g.plane_elems >= (size_t)1 << 32) { hg_set_error("slab too large for 32-bit plane offsets (%zu elements)", c->g.plane_elems); return HG_ERR_INVALID; }
+    {   // ghost rows and peer planes of the previous exchange generation must have landed
+        int rcw = hg_slab_wait_pending(c);
+        if (rcw) return rcw;
+    }
     if (!drops) {
         int rca = align_sets(c);
         if (rca) return rca;

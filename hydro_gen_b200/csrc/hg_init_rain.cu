@@ -66,6 +66,10 @@ int hg_launch_heightmap(hg_ctx* c) {
 }
 
 int hg_launch_rain(hg_ctx* c, float time) {
+    {   // rain is added to the ghost rows too: the neighbours' edge rows of the last exchange must be there first
+        int rcw = hg_slab_wait_pending(c);
+        if (rcw) return rcw;
+    }
     SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
     dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
     // The reference writes the other heightmap texture and swaps (erosion.cpp:76-89).  Rain is

@@ -105,6 +105,7 @@ struct hg_ctx {
     unsigned* h_sticky;        // mapped pinned word raised by a timed-out halo wait (hg_slab.cu); d_sticky = its device alias
     unsigned* d_sticky;
     unsigned long long halo_timeout_ns;
+    uint32_t pending_gen;      // generation signalled but not yet waited for (hg_slab_wait_pending), 0 = none
 };
 
 void hg_set_error(const char* fmt, ...);
@@ -163,5 +164,6 @@ int hg_launch_particle_erode(hg_ctx* c);
 int hg_launch_thermal_smooth_particle(hg_ctx* c);
 int hg_slab_exchange(hg_ctx* c);     // push edge rows to neighbours + wait (no-op without peers)
 int hg_slab_barrier(hg_ctx* c, bool push);   // generation signal + all-rank wait, with or without the edge-row push
+int hg_slab_wait_pending(hg_ctx* c); // enqueue the wait for the last signalled generation (before rain / a step touches the planes)
 int hg_slab_check_sticky(hg_ctx* c); // HG_ERR_STATE once a halo wait has timed out on this context
 void hg_slab_disconnect(hg_ctx* c);

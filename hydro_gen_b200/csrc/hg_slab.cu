@@ -99,6 +99,18 @@ inline size_t plane_elems_of(const hg_ctx* c, int k) { return (size_t)(c->slabs.
 
 }  // namespace
 
+// The sticky error word of k_halo_wait: mapped pinned host memory, so the host reads it without synchronising.
+static int ensure_sticky(hg_ctx* c) {
+    if (c->h_sticky) return HG_OK;
+    HG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_sticky), sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_sticky = 0u;
+    HG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_sticky), c->h_sticky, 0));
+    double s = 60.0;
+    if (const char* e = getenv("HG_HALO_TIMEOUT_S")) { double v = atof(e); if (v > 0.0) s = v; }
+    c->halo_timeout_ns = (unsigned long long)(s * 1e9);
+    return HG_OK;
+}
+
 extern "C" int hg_slab_export_handle(hg_ctx* c, hg_slab_export* out) {
     HG_CHECK_CTX(c);
     if (!out) return HG_ERR_INVALID;
@@ -149,7 +161,7 @@ extern "C" int hg_slab_connect(hg_ctx* c, const hg_slab_export* all, int n, int 
     }
     c->slabs.n = n; c->slabs.me = me;
     c->peers_connected = n > 1;
-    return HG_OK;
+    return ensure_sticky(c);
 }
 
 extern "C" int hg_slab_connect_local(hg_ctx* c, hg_ctx* const* all, int n, int me) {
@@ -179,7 +191,7 @@ extern "C" int hg_slab_connect_local(hg_ctx* c, hg_ctx* const* all, int n, int m
     }
     c->slabs.n = n; c->slabs.me = me;
     c->peers_connected = n > 1;
-    return HG_OK;
+    return ensure_sticky(c);
 }
 
 void hg_slab_disconnect(hg_ctx* c) {
@@ -188,6 +200,7 @@ void hg_slab_disconnect(hg_ctx* c) {
     memset(&c->slabs, 0, sizeof(c->slabs));
     memset(c->slab_ipc, 0, sizeof(c->slab_ipc));
     c->peers_connected = false;
+    c->pending_gen = 0;
 }
 
 extern "C" int hg_slab_errors(hg_ctx* c, uint64_t* count) {
@@ -196,18 +209,6 @@ extern "C" int hg_slab_errors(hg_ctx* c, uint64_t* count) {
     HG_CUDA(cudaMemcpyAsync(&v, c->d_counters + 1, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
     HG_CUDA(cudaStreamSynchronize(c->stream));
     if (count) *count = v;
-    return HG_OK;
-}
-
-// The sticky error word of k_halo_wait: mapped pinned host memory, so the host reads it without synchronising.
-static int ensure_sticky(hg_ctx* c) {
-    if (c->h_sticky) return HG_OK;
-    HG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_sticky), sizeof(unsigned), cudaHostAllocMapped));
-    *c->h_sticky = 0u;
-    HG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_sticky), c->h_sticky, 0));
-    double s = 60.0;
-    if (const char* e = getenv("HG_HALO_TIMEOUT_S")) { double v = atof(e); if (v > 0.0) s = v; }
-    c->halo_timeout_ns = (unsigned long long)(s * 1e9);
     return HG_OK;
 }
 
@@ -222,14 +223,14 @@ int hg_slab_check_sticky(hg_ctx* c) {
 
 int hg_slab_exchange(hg_ctx* c) { return hg_slab_barrier(c, true); }
 
-// After a fused step (push = true): push my new edge rows to both neighbours, publish the generation on
-// every rank, then make this stream wait until every rank has published it.  push = false: only the
+// After a fused step (push = true): push my new edge rows to both neighbours and publish the generation on
+// every rank; the wait until every rank has published it is enqueued in front of the next step (hg_slab_wait_pending).  push = false: only the
 // generation signal + wait, an all-rank barrier on the device (after an in-place rain: a peer's far fetch of
 // the next step must not read this rank's water before the rain has been added).
 int hg_slab_barrier(hg_ctx* c, bool push) {
     if (!c->peers_connected) return HG_OK;
-    int rcs = ensure_sticky(c);
-    if (rcs) return rcs;
+    int rcw = hg_slab_wait_pending(c);      // generations are waited for in order
+    if (rcw) return rcw;
     const HgSlabTable& T = c->slabs;
     c->step_flag++;
     const unsigned gen = c->step_flag;
@@ -252,13 +253,9 @@ int hg_slab_barrier(hg_ctx* c, bool push) {
             A.side[s].dst_off = 0;
         }
     }
-    FlagArgs Wt{};
-    A.sig.n = Wt.n = T.n;
-    for (int k = 0; k < T.n; k++) {
-        if (k == T.me) continue;
-        A.sig.flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);   // my word on rank k
-        Wt.flag[k] = flag_ptr(c->arena, c->g.plane_elems, k);               // rank k's word on me
-    }
+    A.sig.n = T.n;
+    for (int k = 0; k < T.n; k++)
+        if (k != T.me) A.sig.flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);   // my word on rank k
     A.gen = gen;
     A.done = reinterpret_cast<unsigned*>(c->d_counters + 10);
     if (push) {
@@ -269,8 +266,25 @@ int hg_slab_barrier(hg_ctx* c, bool push) {
         k_halo_signal<<<1, 32, 0, c->stream>>>(A.sig, gen);
     }
     HG_LAUNCH_CHECK(c);
-    k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, gen, c->halo_timeout_ns, c->d_counters + 1, c->d_sticky);
+    // The wait for the other ranks' signals is NOT enqueued here but in front of the next kernel that touches the
+    // planes (hg_slab_wait_pending, called by the rain and step launchers): nothing between two steps needs it, the
+    // other ranks get the length of that gap to catch up, and a host thread that drives several slabs of one process
+    // may issue blocking calls (allocations, checkpoint I/O) for slab B while slab A has signalled -- with the spin
+    // kernel already on A's stream those calls would wait for a kernel that waits for B.
+    c->pending_gen = gen;
+    return HG_OK;
+}
+
+int hg_slab_wait_pending(hg_ctx* c) {
+    if (!c->peers_connected || !c->pending_gen) return HG_OK;
+    const HgSlabTable& T = c->slabs;
+    FlagArgs Wt{};
+    Wt.n = T.n;
+    for (int k = 0; k < T.n; k++)
+        if (k != T.me) Wt.flag[k] = flag_ptr(c->arena, c->g.plane_elems, k);      // rank k's word on me
+    k_halo_wait<<<1, 32, 0, c->stream>>>(Wt, c->pending_gen, c->halo_timeout_ns, c->d_counters + 1, c->d_sticky);
     HG_LAUNCH_CHECK(c);
+    c->pending_gen = 0;
     return HG_OK;
 }
 
