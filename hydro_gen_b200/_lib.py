@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhydrogen_b200.so")
+LIB_PATH = os.environ.get("HG_B200_LIB") or os.path.join(_HERE, "libhydrogen_b200.so")      # HG_B200_LIB: another build of the same library (tuning aid)
 
 HG_OK, HG_ERR_INVALID, HG_ERR_CUDA, HG_ERR_STATE, HG_ERR_NO_DEVICE = range(5)
 HG_GRID, HG_PARTICLES = 0, 1

@@ -28,13 +28,13 @@ HG_FN HgFluxOut2 hg_flux_cell2(const HgStepParams& P, B2 x_left, B2 x_right, int
     else if (y >= H - 1) oz = v2s(0.0f);
     const V2 sum_in = inL + inR + inT + inB;
     V2 sum_out = ox + oy + oz + ow;
-    const V2 den = sum_out * P.d_t;
+    const V2 den = (sum_out * P.d_t).v();
     V2 K;
     K.x = hg_min_c(1.0f, hg_div_zero_num(water.x, den.x));
     K.y = hg_min_c(1.0f, hg_div_zero_num(water.y, den.y));
-    ox = ox * K; oy = oy * K; oz = oz * K; ow = ow * K;
-    sum_out = sum_out * K;
-    const V2 d_volume = P.d_t * (sum_in - sum_out);
+    ox = (ox * K).v(); oy = (oy * K).v(); oz = (oz * K).v(); ow = (ow * K).v();
+    const V2P sum_out_k = sum_out * K;
+    const V2P d_volume = P.d_t * (sum_in - sum_out_k);
     const V2 d2 = v2_max_c(0.0f, d1 + d_volume);
     o.fL = ox; o.fR = oy; o.fT = oz; o.fB = ow;
     o.water = d2;
@@ -106,10 +106,10 @@ HG_FN void hg_erosion_cell2(const HgStepParams& P, V2 rock, V2 dirt, V2 sr, V2 s
     const V2 nz = 2.0f * dz - dx * 0.0f;
     const V2 n2 = nx * nx + ny0 * ny0 + nz * nz;
     const V2 inv = v2(1.0f / sqrtf(n2.x), 1.0f / sqrtf(n2.y));
-    const V2 ny = ny0 * inv;
+    const V2 ny = (ny0 * inv).v();
     const V2 s2 = 1.0f - ny * ny;
     const V2 sin_a = v2(fabsf(fabsf(hg_sqrt_pos(s2.x))), fabsf(fabsf(hg_sqrt_pos(s2.y))));
-    const V2 kv = P.Kc * v2_max_c(0.02f, sin_a) * ero_vel;
+    const V2 kv = (P.Kc * v2_max_c(0.02f, sin_a) * ero_vel).v();
     o0 = hg_erosion_layers(P, kv.x, rock.x, dirt.x, sr.x, sd.x);
     o1 = hg_erosion_layers(P, kv.y, rock.y, dirt.y, sr.y, sd.y);
 }
@@ -171,8 +171,8 @@ HG_FN V2 hg_thermal_outflow2(const HgStepParams& P, int layer, V2 own, const V2 
         r = v2_fma(r, v2_fma(nbk, r, v2s(1.0f)), r);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const V2 a = S * d_h[k];
-            const V2 q0 = a * r;
+            const V2 a = (S * d_h[k]).v();
+            const V2 q0 = (a * r).v();
             const V2 q = v2_fma(r, v2_fma(nbk, q0, a), q0);
             out[k] = v2_sel(mark[k], q, 0.0f);
             neg = neg - out[k];
@@ -221,14 +221,14 @@ HG_FN V2 hg_thermal_delta2(V2 neg_out, V2 fromL, V2 fromR, V2 fromT, V2 fromB, V
 // ---------------------------------------------------------------- smoothing.glsl:22-75, both lanes (interior cells)
 HG_FN V2 hg_div5_2(V2 x) {
 #if HG_DEVICE_FAST
-    const V2 q = x * 0.2f;
+    const V2 q = (x * 0.2f).v();
     return v2_fma(v2_fma(v2s(-5.0f), q, x), v2s(0.2f), q);
 #else
     return v2(x.x / 5.0f, x.y / 5.0f);
 #endif
 }
 HG_FN B2 hg_smooth_extremum(V2 dl, V2 dr, V2 dt, V2 db, V2 hdiff) {
-    const V2 xc = dl * dr, yc = dt * db;
+    const V2 xc = (dl * dr).v(), yc = (dt * db).v();
     B2 m;
     m.x = (((-dl.x) > hdiff.x || (-dr.x) > hdiff.x) && xc.x > 0.0f) || (((-dt.x) > hdiff.x || (-db.x) > hdiff.x) && yc.x > 0.0f);
     m.y = (((-dl.y) > hdiff.y || (-dr.y) > hdiff.y) && xc.y > 0.0f) || (((-dt.y) > hdiff.y || (-db.y) > hdiff.y) && yc.y > 0.0f);
@@ -240,8 +240,8 @@ HG_FN void hg_smooth_cell2(const HgStepParams& P, V2& rock, V2& dirt, V2 lr, V2 
     const V2 drr = terr_r - rr; V2 drg = terr_g - rg; drg = drg + drr;
     const V2 dtr = terr_r - tr; V2 dtg = terr_g - tg; dtg = dtg + dtr;
     const V2 dbr = terr_r - br; V2 dbg = terr_g - bg; dbg = dbg + dbr;
-    V2 g_hdiff = (dlg + drg + dtg + dbg) * 0.25f;      // x / 4 and x * 0.25 round identically (exact scaling by a power of two)
-    V2 r_hdiff = (dlr + drr + dtr + dbr) * 0.25f;
+    V2 g_hdiff = ((dlg + drg + dtg + dbg) * 0.25f).v();      // x / 4 and x * 0.25 round identically (exact scaling by a power of two)
+    V2 r_hdiff = ((dlr + drr + dtr + dbr) * 0.25f).v();
     g_hdiff = v2(fabsf(g_hdiff.x), fabsf(g_hdiff.y));
     r_hdiff = v2(fabsf(r_hdiff.x), fabsf(r_hdiff.y));
     const B2 mr = hg_smooth_extremum(dlr, drr, dtr, dbr, r_hdiff);

@@ -25,6 +25,7 @@
 #include <vector>
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
+#include "hg_fused_body2.cuh"
 #include "hg_plan.cuh"
 
 #ifndef HG_FREE_UNROLL
@@ -32,6 +33,9 @@
 #endif
 constexpr int kFreeUnroll = HG_FREE_UNROLL;
 constexpr int HG_MAX_DEVICES = 64;
+#ifndef HG_FUSED_DEFAULT_VARIANT
+#define HG_FUSED_DEFAULT_VARIANT 5     // 5: one column per thread (k_fused_ws); 10: two columns per thread (k_fused_ws2)
+#endif
 
 namespace {
 
@@ -325,6 +329,97 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------ two columns per thread (hg_fused_body2.cuh)
+// Same warp-specialised shell; a CTA of 2*NT threads owns a PAIR of adjacent strips and every thread carries column t
+// of both strips in the two lanes of packed fp32 arithmetic.  One TMA box per row covers both strips
+// (2*NT - 8 columns x 9 planes).
+template <int NT> struct FusedSmem2 {
+    static constexpr size_t RAW_BOX = (size_t)HGF_NPL * HGF2_RAW_LD(NT);
+    static constexpr size_t RAW_SLOT = (RAW_BOX + 31) / 32 * 32;
+    static constexpr size_t RINGS = 2 * RAW_SLOT;
+    static constexpr size_t BARS = (RINGS + HgRings2<NT>::TOTAL + 3) / 4 * 4;
+    static constexpr size_t BYTES = (BARS + 4) * sizeof(float);
+};
+
+template <int NT, int MINB, int RH, int RT>
+__global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws2(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smb[];
+    float* const sm = smb + FusedSmem2<NT>::RINGS;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem2<NT>::BARS);
+    const bool hydro = threadIdx.x < NT;
+    const int tid = hydro ? threadIdx.x : threadIdx.x - NT;
+    int strip, gy0, gy1;      // strip = index of the strip PAIR
+    if (K.plan) {
+        const HgPlanItem it = K.plan[blockIdx.x];
+        strip = it.strip; gy0 = it.gy0; gy1 = it.gy1;
+    } else {
+        const int segi = blockIdx.x / K.nstrips;
+        strip = blockIdx.x % K.nstrips;
+        gy0 = K.row0 + segi * K.seg;
+        gy1 = min(gy0 + K.seg, K.row0 + K.rows);
+    }
+    unsigned long long t_start = 0;
+    if (K.cta_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    constexpr int HALF = HGF2_HALF(NT);
+    const int x0 = strip * (2 * HALF) - HGF_HX;
+    const HgLanes L = hg_lanes(x0 + tid, HALF, tid, NT, K.W);
+    const HgFusedPlan pl = hg_fused_plan(gy0, gy1, K.H);
+    const unsigned pitch = (unsigned)K.pitch;
+    unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)(x0 + tid);
+    const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
+    constexpr unsigned BOX_BYTES = (unsigned)(FusedSmem2<NT>::RAW_BOX * sizeof(float));
+    const int bx0 = x0 - 2;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], BOX_BYTES);
+        tma_load_3d(smb, &tmap, &bars[0], bx0, ly0, 0);
+    }
+    __syncthreads();
+    HgCol2 c;
+    hg_col2_init(c);
+    int i = pl.i_begin;
+    if (hydro) {
+        if (RH != RT) reg_dec<RH>();
+#define HG_ROW_H(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        const int rel = i - pl.i_begin;                                                                              \
+        if (tid == 0 && i < pl.i_end) {                                                                              \
+            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
+            tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem2<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
+        }                                                                                                            \
+        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        hg_fused_iter2<NT, FREEFLAG, HGF_HYDRO>(c, sm, smb + (rel & 1) * FusedSmem2<NT>::RAW_SLOT, K, tid, L, gy0, gy1, i, off); \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#undef HG_ROW_H
+        if (K.cta_ns && threadIdx.x == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
+        }
+    } else {
+        if (RH != RT) reg_inc<RT>();
+#define HG_ROW_T(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        hg_fused_iter2<NT, FREEFLAG, HGF_THERMAL>(c, sm, smb, K, tid, L, gy0, gy1, i, off);                          \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#undef HG_ROW_T
+    }
+}
+
 // ------------------------------------------------------------------ balanced partition
 // All CTAs of a step are resident at once (one wave, 3 per SM), so the step ends when the SLOWEST CTA
 // ends.  With equal segments of rows that was 0.69 ms at 4096^2 while the mean CTA took 0.55 ms: the
@@ -393,7 +488,7 @@ __global__ void __launch_bounds__(512) k_plan_segments(PlanArgs A) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int make_tmap(hg_ctx* c, int set, int nt, CUtensorMap* out) {
+static int make_tmap(hg_ctx* c, int set, int box_cols, CUtensorMap* out) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -404,12 +499,12 @@ static int make_tmap(hg_ctx* c, int set, int nt, CUtensorMap* out) {
     }
     cuuint64_t dims[3] = {(cuuint64_t)c->g.W, (cuuint64_t)c->g.rows_alloc, (cuuint64_t)HG_NPLANES};
     cuuint64_t strides[2] = {(cuuint64_t)c->g.pitch * sizeof(float), (cuuint64_t)c->g.plane_elems * sizeof(float)};
-    cuuint32_t box[3] = {(cuuint32_t)HGF_RAW_LD(nt), 1u, (cuuint32_t)HG_NPLANES};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, 1u, (cuuint32_t)HG_NPLANES};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, hg_plane(c, set, 0), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { hg_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d slab, box %d", (int)r, c->g.W, c->g.rows_alloc, nt); return HG_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { hg_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d slab, box %d", (int)r, c->g.W, c->g.rows_alloc, box_cols); return HG_ERR_CUDA; }
     return HG_OK;
 }
 
@@ -427,7 +522,7 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
         if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(c, src_set, NT, &tmap);
+    int rc = make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
     k_fused_step<NT, MINB><<<K.nstrips * nseg, NT, smem, c->stream>>>(K, tmap);
@@ -450,10 +545,35 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
         if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(c, src_set, NT, &tmap);
+    int rc = make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
     k_fused_ws<NT, MINB, RH, RT, DROPS><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
+    HG_LAUNCH_CHECK(c);
+    if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
+    return HG_OK;
+}
+
+
+// two columns per thread: the strips of the launch are strip PAIRS of 2 * (NT - 12) owned columns
+template <int NT, int MINB, int RH, int RT>
+static int launch_ws2(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
+    static_assert((RH + RT) / 2 * 2 * NT * MINB <= 65536 && RH % 8 == 0 && RT % 8 == 0, "register budget of the two warp groups");
+    HgFusedK K = K0;
+    K.nstrips = (c->g.W + 2 * HGF2_HALF(NT) - 1) / (2 * HGF2_HALF(NT));
+    K.seg = seg;
+    int nseg = (c->g.rows + seg - 1) / seg;
+    constexpr size_t smem = FusedSmem2<NT>::BYTES;
+    static bool attr_set[HG_MAX_DEVICES] = {};
+    if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
+        HG_CUDA(cudaFuncSetAttribute(k_fused_ws2<NT, MINB, RH, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
+    }
+    alignas(64) CUtensorMap tmap;
+    int rc = make_tmap(c, src_set, HGF2_RAW_LD(NT), &tmap);
+    if (rc) return rc;
+    if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
+    k_fused_ws2<NT, MINB, RH, RT><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
@@ -525,13 +645,17 @@ static int launch_fused(hg_ctx* c, bool drops) {
     }
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
     // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA
-    static const int nt_of[] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128};
-    static const int res_of[] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4};
-    static const int wpc_of[] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8};
-    int v = c->tune_variant >= 0 && c->tune_variant < 10 ? c->tune_variant : 5;   // default: warp-specialised, 3 CTAs per SM
+    // variants 10..: two columns per thread (k_fused_ws2): strip pairs, 2 CTAs of 256 threads per SM
+    constexpr int NVAR = 13;
+    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128};
+    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2};
+    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8};
+    int v = c->tune_variant >= 0 && c->tune_variant < NVAR ? c->tune_variant : HG_FUSED_DEFAULT_VARIANT;
     if (drops) v = 5;
+    const bool two_lane = v >= 10;
     const int NT = nt_of[v];
-    int nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
+    const int strip_w = two_lane ? 2 * HGF2_HALF(NT) : NT - 2 * HGF_HX;      // owned columns per CTA
+    int nstrips = (c->g.W + strip_w - 1) / strip_w;
     // Rows per CTA.  A CTA runs seg + 17 row iterations (pipeline fill), about 8 of them of the
     // slower non-FREE kind.  An SM's time for a wave of w resident warps was measured as roughly
     // proportional to 10 + 0.375 w per row iteration (8 warps reach 61 % of the throughput of 16).
@@ -555,14 +679,14 @@ static int launch_fused(hg_ctx* c, bool drops) {
     // HG_FUSED_BALANCE=0 keep the uniform segments.
     bool balanced = false;
     PlanArgs plan_args{};
-    if (v == 5 && c->tune_seg <= 0 && !c->no_balance) {
+    if ((v == 5 || two_lane) && c->tune_seg <= 0 && !c->no_balance) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // Only with at least six segments per strip: with fewer (16384 columns: 3.1 per strip) one segment more or
         // less is too coarse a step, and moving only the cuts inside a strip was measured 5 % SLOWER than uniform
         // segments there (CTAs of 5000 rows already average the terrain; the forecast then mostly carries noise).
         const int min_rows = 48;
-        const int n_cta = 3 * sms;
+        const int n_cta = res_of[v] * sms;
         if (n_cta / nstrips >= 6 && (long long)nstrips * (c->g.rows / min_rows) >= 2LL * n_cta) {
             if (!c->plan[0]) {      // first use: uniform cut into n_cta pieces (strip k gets n_cta/nstrips, the first few one more)
                 HG_CUDA(cudaMalloc(&c->plan[0], 2 * n_cta * sizeof(HgPlanItem)));
@@ -604,7 +728,10 @@ static int launch_fused(hg_ctx* c, bool drops) {
     case 6: rc = launch_ws<128, 2, 96, 128>(c, K, seg, c->ri[0]); break;
     case 7: rc = launch_ws<128, 3, 64, 96>(c, K, seg, c->ri[0]); break;
     case 8: rc = launch_ws<128, 4, 64, 64>(c, K, seg, c->ri[0]); break;
-    default: rc = launch_ws<128, 4, 56, 72>(c, K, seg, c->ri[0]); break;
+    case 9: rc = launch_ws<128, 4, 56, 72>(c, K, seg, c->ri[0]); break;
+    case 10: rc = launch_ws2<128, 2, 120, 136>(c, K, seg, c->ri[0]); break;
+    case 11: rc = launch_ws2<128, 2, 128, 128>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_ws2<128, 2, 112, 144>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     if (balanced) {

@@ -9,6 +9,7 @@
 #include "../../hydro_gen_b200/csrc/hg_cell.cuh"
 #include "../../hydro_gen_b200/csrc/hg_noise.cuh"
 #include "../../hydro_gen_b200/csrc/hg_fused_body.cuh"
+#include "../../hydro_gen_b200/csrc/hg_fused_body2.cuh"
 
 namespace {
 struct Dom { int W, H; };
@@ -189,6 +190,74 @@ extern "C" long emul_fused_step(const hg_erosion_data* set, int W, int H, int nt
     if (nt == 32) return fused_step_emul<32>(set, W, H, seg, ws, src, dst, far_out);
     if (nt == 128) return fused_step_emul<128>(set, W, H, seg, ws, src, dst, far_out);
     if (nt == 224) return fused_step_emul<224>(set, W, H, seg, ws, src, dst, far_out);
+    return -1;
+}
+
+
+// The two-columns-per-thread body (hg_fused_body2.cuh, k_fused_ws2) run the same way: a CTA owns a pair of strips,
+// thread t carries column t of both in the two lanes of a V2 (scalar pairs on the host).  ws as above.
+template <int NT>
+static long fused2_step_emul(const hg_erosion_data* set, int W, int H, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    const int HALO = 8;
+    constexpr int HALF = HGF2_HALF(NT), LD = HGF2_RAW_LD(NT);
+    size_t pe = (size_t)(H + 2 * HALO) * W;
+    std::vector<std::vector<float>> ps(9, std::vector<float>(pe, 0.0f)), pd(9, std::vector<float>(pe, 0.0f));
+    for (int p = 0; p < 9; p++) memcpy(ps[p].data() + (size_t)HALO * W, src[p], (size_t)W * H * 4);
+    unsigned long long far_count = 0;
+    HgFusedK K;
+    memset(&K, 0, sizeof(K));
+    for (int p = 0; p < 9; p++) { K.src[p] = ps[p].data(); K.dst[p] = pd[p].data(); }
+    K.W = W; K.H = H; K.row0 = 0; K.rows = H; K.pitch = W; K.seg = seg;
+    K.nstrips = (W + 2 * HALF - 1) / (2 * HALF);
+    K.far_list = far_out; K.far_count = &far_count;
+    K.P = hg_make_step_params(*set);
+    int nseg = (H + seg - 1) / seg;
+    std::vector<float> sm(HgRings2<NT>::TOTAL + 8);
+    std::vector<HgCol2> cols(NT), colsT(NT);
+    for (int blk = 0; blk < K.nstrips * nseg; blk++) {
+        std::fill(sm.begin(), sm.end(), 0.0f);
+        float* smp = sm.data();
+        while ((uintptr_t)smp % 16) smp++;
+        int strip = blk % K.nstrips, segi = blk / K.nstrips;
+        int gy0 = segi * seg, gy1 = gy0 + seg < H ? gy0 + seg : H;
+        HgFusedPlan pl = hg_fused_plan(gy0, gy1, H);
+        const int x0 = strip * (2 * HALF) - HGF_HX;
+        for (int tid = 0; tid < NT; tid++) { hg_col2_init(cols[tid]); hg_col2_init(colsT[tid]); }
+        std::vector<float> raw(9 * LD);
+        for (int i = pl.i_begin; i <= pl.i_end; i++) {
+            bool fr = i >= pl.free_lo && i <= pl.free_hi;
+            for (int p = 0; p < 9; p++) for (int t = 0; t < LD; t++) {
+                int x = x0 - 2 + t, lr = i + HALO;
+                raw[p * LD + t] = (x >= 0 && x < W && lr >= 0 && lr < H + 2 * HALO) ? ps[p][(size_t)lr * W + x] : 0.0f;
+            }
+            auto run_group = [&](int group) {
+                for (int tid = 0; tid < NT; tid++) {
+                    const HgLanes L = hg_lanes(x0 + tid, HALF, tid, NT, W);
+                    unsigned off = (unsigned)(i + HALO) * (unsigned)W + (unsigned)(x0 + tid);
+                    if (group == HGF_ALL) {
+                        if (fr) hg_fused_iter2<NT, true, HGF_ALL>(cols[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                        else hg_fused_iter2<NT, false, HGF_ALL>(cols[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                    } else if (group == HGF_HYDRO) {
+                        if (fr) hg_fused_iter2<NT, true, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                        else hg_fused_iter2<NT, false, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                    } else {
+                        if (fr) hg_fused_iter2<NT, true, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                        else hg_fused_iter2<NT, false, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, L, gy0, gy1, i, off);
+                    }
+                }
+            };
+            if (ws == 0) run_group(HGF_ALL);
+            else if (ws == 1) { run_group(HGF_HYDRO); run_group(HGF_THERMAL); }
+            else { run_group(HGF_THERMAL); run_group(HGF_HYDRO); }
+        }
+    }
+    for (int p = 0; p < 9; p++) memcpy(dst[p], pd[p].data() + (size_t)HALO * W, (size_t)W * H * 4);
+    return (long)far_count;
+}
+
+extern "C" long emul_fused2_step(const hg_erosion_data* set, int W, int H, int nt, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    if (nt == 32) return fused2_step_emul<32>(set, W, H, seg, ws, src, dst, far_out);
+    if (nt == 128) return fused2_step_emul<128>(set, W, H, seg, ws, src, dst, far_out);
     return -1;
 }
 

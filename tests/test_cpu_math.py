@@ -139,7 +139,7 @@ def test_struct_layouts_match_the_reference():
     assert oracle.PARTICLE_DTYPE.fields["sediment"][1] == 32 and oracle.PARTICLE_DTYPE.fields["to_kill"][1] == 40
 
 
-def fused_emul_step(E, w, nt, seg, ws=0):
+def fused_emul_step(E, w, nt, seg, ws=0, two_lane=False):
     """one step of the fused kernel body on the CPU; returns (planes, far cell indices)"""
     src = planes_of(w)
     dst = [np.zeros_like(p) for p in src]
@@ -147,8 +147,9 @@ def fused_emul_step(E, w, nt, seg, ws=0):
     sa = (C.c_void_p * 9)(*[p.ctypes.data for p in src])
     da = (C.c_void_p * 9)(*[p.ctypes.data for p in dst])
     er = hl.ErosionData.from_buffer_copy(bytes(w.erosion))
-    E.emul_fused_step.restype = C.c_long
-    n = E.emul_fused_step(C.byref(er), w.W, w.H, nt, seg, ws, sa, da, far.ctypes.data_as(C.c_void_p))
+    fn = E.emul_fused2_step if two_lane else E.emul_fused_step
+    fn.restype = C.c_long
+    n = fn(C.byref(er), w.W, w.H, nt, seg, ws, sa, da, far.ctypes.data_as(C.c_void_p))
     assert n >= 0
     return dst, far[:n]
 
@@ -177,4 +178,53 @@ def test_fused_kernel_body_emulated_matches_oracle(emul, nt, seg, shape, ws):
                 g = np.where(mask.reshape(H, W), g, x)
             assert_bit_equal(g, x, f"nt={nt} seg={seg} {name}")
         total_far += len(far)
+    w.close()
+
+
+@pytest.mark.parametrize("nt,seg,shape,ws", [(32, 16, (72, 64), 0), (32, 64, (40, 136), 1), (32, 16, (104, 64), 2), (128, 32, (192, 96), 1),
+                                             (128, 128, (256, 160), 2), (128, 48, (504, 64), 1)])
+def test_two_lane_fused_body_emulated_matches_oracle(emul, nt, seg, shape, ws):
+    """hg_fused_body2.cuh -- the code k_fused_ws2 runs: every thread advances column t of TWO adjacent strips in the
+    two lanes of packed fp32 arithmetic (hg_v2.cuh, hg_cell2.cuh) -- executed thread by thread on the CPU (the packed
+    operations as two scalar ones), single group and the warp-specialised split in either group order, against the
+    oracle: every plane bit-exact, the deferred far cells exactly the cells whose back-trace leaves the +-1 window.
+    Widths with a half-empty last strip pair, exactly two pairs, and one pair."""
+    W, H = shape
+    w = wet_world(H, 120, width=W, period=8)
+    names = "rock dirt water fL fR fT fB sed_r sed_d".split()
+    for _ in range(3):
+        got, far = fused_emul_step(emul, w, nt, seg, ws, two_lane=True)
+        pl = planes_of(w)
+        far_ref = emul_step(emul, w, pl)
+        w.step((w.steps + 1) * DT_TIME)
+        want = planes_of(w)
+        assert len(far) == far_ref
+        mask = np.ones(W * H, bool); mask[far] = False
+        for k, (g, x, name) in enumerate(zip(got, want, names)):
+            if k >= 7:
+                g = np.where(mask.reshape(H, W), g, x)
+            assert_bit_equal(g, x, f"two-lane nt={nt} seg={seg} {name}")
+    w.close()
+
+
+def test_two_lane_thermal_marking_matches_oracle_steep(emul):
+    """the packed thermal outflow (hg_thermal_outflow2: one lane hot, both hot, none) on roughened terrain with lowered
+    talus angles, several parameter sets"""
+    n = 96
+    w = oracle.World(n, seed=SEED); w.gen_heightmap()
+    H = w.get(0)
+    rng = np.random.default_rng(3)
+    H[..., 0] += rng.random((n, n), dtype=np.float32) * 6
+    H[..., 1] += rng.random((n, n), dtype=np.float32) * 2
+    H[..., 3] = H[..., 0] + H[..., 1] + H[..., 2]
+    w.set(0, H)
+    names = "rock dirt water fL fR fT fB sed_r sed_d".split()
+    for ka in ((0.9, 0.3), (1.3, 0.6), (0.05, 1.55)):
+        w.erosion.Kalpha[0], w.erosion.Kalpha[1] = ka
+        for _ in range(2):
+            got, far = fused_emul_step(emul, w, 32, 48, 1, two_lane=True)
+            assert len(far) == 0
+            w.dispatch_grid()
+            for g, x, name in zip(got, planes_of(w), names):
+                assert_bit_equal(g, x, f"two-lane Kalpha={ka}: {name}")
     w.close()
