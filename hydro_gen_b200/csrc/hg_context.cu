@@ -28,6 +28,10 @@ static void free_ctx(hg_ctx* c) {
     if (c->arena) cudaFree(c->arena);
     if (c->aux) cudaFree(c->aux);
     if (c->particles) cudaFree(c->particles);
+    if (c->pa) cudaFree(c->pa);
+    if (c->p_order) cudaFree(c->p_order);
+    if (c->p_keys) cudaFree(c->p_keys);
+    if (c->p_hist) cudaFree(c->p_hist);
     if (c->lockmap) cudaFree(c->lockmap);
     if (c->staging) cudaFree(c->staging);
     if (c->stage_up) cudaFree(c->stage_up);
@@ -128,6 +132,8 @@ extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0,
     if (const char* e = getenv("HG_FUSED_SEG")) c->tune_seg = atoi(e);   // tuning aids
     if (const char* e = getenv("HG_FUSED_VARIANT")) c->tune_variant = atoi(e);
     if (const char* e = getenv("HG_FUSED_BALANCE")) c->no_balance = atoi(e) == 0;
+    c->p_rebin_period = 8;
+    if (const char* e = getenv("HG_DROPS_REBIN")) c->p_rebin_period = atoi(e);
     refresh_params(c);
     if (create_impl(c) != HG_OK) { free_ctx(c); return nullptr; }
     return c;
@@ -181,6 +187,48 @@ extern "C" int hg_set_schedule(hg_ctx* c, int schedule) {
         }
     }
     c->schedule = schedule;
+    return HG_OK;
+}
+
+// ------------------------------------------------------------- droplet-mode layouts
+namespace {
+struct LayoutPlanes { float *rock, *dirt, *water, *total, *m[4]; };
+__global__ void __launch_bounds__(256) k_planes_to_aos(LayoutPlanes P, float4* ha, float4* ma, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        ha[i] = make_float4(P.rock[i], P.dirt[i], P.water[i], P.total[i]);
+        ma[i] = make_float4(P.m[0][i], P.m[1][i], P.m[2][i], P.m[3][i]);
+    }
+}
+__global__ void __launch_bounds__(256) k_aos_to_planes(LayoutPlanes P, const float4* ha, const float4* ma, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 h = ha[i], m = ma[i];
+        P.rock[i] = h.x; P.dirt[i] = h.y; P.water[i] = h.z; P.total[i] = h.w;
+        P.m[0][i] = m.x; P.m[1][i] = m.y; P.m[2][i] = m.z; P.m[3][i] = m.w;
+    }
+}
+}  // namespace
+
+// The droplet kernels gather and scatter single texels at random positions: with one 16-byte texel per cell a droplet
+// touches ~11 DRAM sectors per step instead of 81 with five separate planes, and its deposits are two vector
+// reductions per corner instead of five scalar ones.  So in droplet mode the product path (move, erode, fused
+// thermal/smoothing tail) works on H and M in the reference's own texture layout; the 1:1 pass kernels, heightmap
+// init and the mass diagnostic keep the planes.  Only the read images / planes are converted (a step writes the
+// other set completely).
+int hg_particle_layout(hg_ctx* c, bool want_aos) {
+    if (c->erosion_type != HG_PARTICLES || c->p_aos == want_aos) return HG_OK;
+    int rc = hg_ensure_aux(c);
+    if (rc) return rc;
+    if (!c->pa) {
+        HG_CUDA(cudaMalloc(&c->pa, (size_t)4 * c->g.plane_elems * sizeof(float4)));
+        HG_CUDA(cudaMemsetAsync(c->pa, 0, (size_t)4 * c->g.plane_elems * sizeof(float4), c->stream));
+    }
+    LayoutPlanes P{hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1), hg_total(c, 1),
+                   {hg_vel(c, 0, 1), hg_vel(c, 1, 1), hg_vel(c, 2, 1), hg_vel(c, 3, 1)}};
+    const size_t n = c->g.plane_elems;
+    if (want_aos) k_planes_to_aos<<<148 * 8, 256, 0, c->stream>>>(P, hg_pa_h(c, 1), hg_pa_m(c, 1), n);
+    else k_aos_to_planes<<<148 * 8, 256, 0, c->stream>>>(P, hg_pa_h(c, 1), hg_pa_m(c, 1), n);
+    HG_LAUNCH_CHECK(c);
+    c->p_aos = want_aos;
     return HG_OK;
 }
 
@@ -284,6 +332,14 @@ int ensure_staging(hg_ctx* c) {
 
 int transfer(hg_ctx* c, int field, float* host, bool upload) {
     if (!host) { hg_set_error("null host buffer"); return HG_ERR_INVALID; }
+    if (c->p_aos && (field == HG_FIELD_HEIGHTMAP || field == HG_FIELD_VELOCITY)) {
+        // droplet mode, texture layout: the image IS the reference's RGBA32F texture; the owned rows are contiguous
+        float4* img = (field == HG_FIELD_HEIGHTMAP ? hg_pa_h(c, 1) : hg_pa_m(c, 1)) + (size_t)HG_HALO_ROWS * c->g.pitch;
+        const size_t bytes = (size_t)c->g.rows * c->g.W * 4 * sizeof(float);
+        if (upload) HG_CUDA(cudaMemcpyAsync(img, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        else HG_CUDA(cudaMemcpyAsync(host, img, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return HG_OK;
+    }
     Chan4 ch; int synth;
     int rc = field_channels(c, field, &ch, &synth, upload);
     if (rc) return rc;
@@ -348,6 +404,7 @@ extern "C" int hg_upload_particles(hg_ctx* c, const hg_particle* src, uint32_t c
     HG_CHECK_CTX(c);
     if (!src || count > c->particle_count) { hg_set_error("bad particle upload (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
     HG_CUDA(cudaMemcpyAsync(c->particles, src, (size_t)count * sizeof(hg_particle), cudaMemcpyHostToDevice, c->stream));
+    c->p_order_valid = false;      // positions changed under the processing order
     HG_CUDA(cudaStreamSynchronize(c->stream));
     return HG_OK;
 }
@@ -369,6 +426,10 @@ extern "C" void hg_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int hg_mass(hg_ctx* c, double out5[5]) {
     HG_CHECK_CTX(c);
     if (!out5) return HG_ERR_INVALID;
+    {
+        int rcl = hg_particle_layout(c, false);
+        if (rcl) return rcl;
+    }
     double* d = reinterpret_cast<double*>(c->d_counters + 2);
     HG_CUDA(cudaMemsetAsync(d, 0, 5 * sizeof(double), c->stream));
     k_mass<<<148 * 8, 256, 0, c->stream>>>(hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1),

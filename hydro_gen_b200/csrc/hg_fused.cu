@@ -277,28 +277,31 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     const unsigned pitch = (unsigned)K.pitch;
     unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
     const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
-    constexpr unsigned BOX_BYTES = (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
+    // grid step: box = (NT+4 columns) x 1 row x 9 planes at (column, row, plane 0); droplet mode: box = 4 channels x
+    // (NT+4 texels) x 1 row of the heightmap in texture layout at (channel 0, column, row)
+    constexpr unsigned BOX_BYTES = DROPS ? (unsigned)(HGF_RAW_LD(NT) * 4 * sizeof(float)) : (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
     const int bx0 = x0 - 2;
+#define HG_TMA_ROW(dst, bar, row) (DROPS ? tma_load_3d((dst), &tmap, (bar), 0, bx0, (row)) : tma_load_3d((dst), &tmap, (bar), bx0, (row), 0))
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bars[0], BOX_BYTES);
-        tma_load_3d(smb, &tmap, &bars[0], bx0, ly0, 0);
+        HG_TMA_ROW(smb, &bars[0], ly0);
     }
     __syncthreads();
     HgCol c;
     hg_fused_begin(c);
     int i = pl.i_begin;
     if (hydro) {
-        if (RH != RT) reg_dec<RH>();
+        if (RH < RT) reg_dec<RH>(); else if (RH > RT) reg_inc<RH>();      // droplet mode gives the hydraulic group the larger share
 #define HG_ROW_H(FREEFLAG)                                                                                           \
     {                                                                                                                \
         const int rel = i - pl.i_begin;                                                                              \
         if (tid == 0 && i < pl.i_end) {                                                                              \
             mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
-            tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
+            HG_TMA_ROW(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &bars[(rel + 1) & 1], ly0 + rel + 1);       \
         }                                                                                                            \
         mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
         hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
             K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
         }
     } else {
-        if (RH != RT) reg_inc<RT>();
+        if (RH < RT) reg_inc<RT>(); else if (RH > RT) reg_dec<RT>();
 #define HG_ROW_T(FREEFLAG)                                                                                           \
     {                                                                                                                \
         hg_fused_iter<NT, FREEFLAG, HGF_THERMAL, DROPS>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
 #undef HG_ROW_T
+#undef HG_TMA_ROW
     }
 }
 
@@ -508,6 +512,27 @@ static int make_tmap(hg_ctx* c, int set, int box_cols, CUtensorMap* out) {
     return HG_OK;
 }
 
+// 3-D tensor map over one heightmap image in texture layout (droplet mode): (channel, column, row), box 4 x (NT+4) x 1.
+static int make_tmap_aos(hg_ctx* c, const float4* image, int box_cols, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { hg_set_error("cuTensorMapEncodeTiled is not available in this driver"); return HG_ERR_CUDA; }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cuuint64_t dims[3] = {4u, (cuuint64_t)c->g.W, (cuuint64_t)c->g.rows_alloc};
+    cuuint64_t strides[2] = {4 * sizeof(float), (cuuint64_t)c->g.pitch * 4 * sizeof(float)};
+    cuuint32_t box[3] = {4u, (cuuint32_t)box_cols, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float4*>(image), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { hg_set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d texel image, box %d", (int)r, c->g.W, c->g.rows_alloc, box_cols); return HG_ERR_CUDA; }
+    return HG_OK;
+}
+
 // NT threads per CTA; seg rows per CTA.
 template <int NT, int MINB>
 static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
@@ -545,7 +570,7 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
         if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
+    int rc = DROPS ? make_tmap_aos(c, reinterpret_cast<const float4*>(K.ha_src), HGF_RAW_LD(NT), &tmap) : make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
     k_fused_ws<NT, MINB, RH, RT, DROPS><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
@@ -638,10 +663,11 @@ static int launch_fused(hg_ctx* c, bool drops) {
     c->far_parity ^= 1;
     A.P = K.P = c->sp;
     if (drops) {
-        // the nine-plane TMA box is read from H's set (only rock and dirt are used); F and S are not touched
-        for (int p = 0; p < HG_NPLANES; p++) { K.src[p] = hg_plane(c, c->ri[0], p); K.dst[p] = hg_plane(c, c->ri[0] ^ 1, p); }
-        for (int k = 0; k < 4; k++) { K.msrc[k] = hg_vel(c, k, 1); K.mdst[k] = hg_vel(c, k, 0); }
-        K.total_dst = hg_total(c, 0);
+        // heightmap and momentum map in texture layout (hg_particle_layout): read images -> write images
+        int rcl = hg_particle_layout(c, true);
+        if (rcl) return rcl;
+        K.ha_src = reinterpret_cast<const HgF4*>(hg_pa_h(c, 1)); K.ha_dst = reinterpret_cast<HgF4*>(hg_pa_h(c, 0));
+        K.ma_src = reinterpret_cast<const HgF4*>(hg_pa_m(c, 1)); K.ma_dst = reinterpret_cast<HgF4*>(hg_pa_m(c, 0));
     }
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
     // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA

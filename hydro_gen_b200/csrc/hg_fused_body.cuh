@@ -51,9 +51,11 @@
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
 #define HGF_LDG(p) __ldg(p)
+#define HGF_LDG4(p) hg_ldg_f4(p)
 #define HGF_ATOMIC_INC64(p) atomicAdd((p), 1ull)
 #else
 #define HGF_LDG(p) (*(p))
+#define HGF_LDG4(p) (*(p))
 #define HGF_ATOMIC_INC64(p) ((*(p))++)
 #endif
 
@@ -66,8 +68,11 @@ constexpr int HGF_LAG_G = 11;    // rows between L and G
 constexpr int HGF_NPL = 9;       // rock dirt water fL fR fT fB sr sd (HgPlane order)
 #define HGF_RAW_LD(NT) ((NT) + 4)  // columns per plane row in the TMA-staged raw block
 
-struct HgF4 { float x, y, z, w; };
-struct HgF2 { float x, y; };
+struct alignas(16) HgF4 { float x, y, z, w; };
+struct alignas(8) HgF2 { float x, y; };
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ HgF4 hg_ldg_f4(const HgF4* p) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); HgF4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+#endif
 #if defined(__CUDACC__)
 static_assert(sizeof(HgF4) == 16 && sizeof(HgF2) == 8, "packed ring elements");
 #endif
@@ -106,10 +111,12 @@ struct HgFusedK {
     // duration in cta_ns[b]; null = uniform segments of `seg` rows
     const HgPlanItem* plan;
     unsigned* cta_ns;
-    // droplet mode (DROPS): the momentum map (4 channels) and H.a planes read / written by the smoothing stage
-    const float* msrc[4];
-    float* mdst[4];
-    float* total_dst;
+    // droplet mode (DROPS): heightmap and momentum map in the reference's texture layout (one 16-byte texel per cell:
+    // (rock, dirt, water, total) and (mx, my, acc_x, acc_y)), the layout the droplet kernels gather from and scatter to
+    const HgF4* ha_src;
+    HgF4* ha_dst;
+    const HgF4* ma_src;
+    HgF4* ma_dst;
     HgStepParams P;
 };
 
@@ -171,9 +178,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     // left: this group only feeds the thermal group with (rock, dirt) of row i-1, as stage A does with (rockE, dirtE).
     c.rk1 = c.rk2; c.dt1 = c.dt2;
     {
-        const float* rw = raw + tid + 2;
-        constexpr int LD = HGF_RAW_LD(NT);
-        c.rk2 = rw[0 * LD]; c.dt2 = rw[1 * LD];
+        // raw row i: NT+4 heightmap texels (rock, dirt, water, total), staged by one TMA box load
+        const HgF4 t = reinterpret_cast<const HgF4*>(raw)[tid + 2];
+        c.rk2 = t.x; c.dt2 = t.y;
     }
     {
         const int ya = i - 1;
@@ -352,6 +359,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     }   // GROUP != HGF_HYDRO
 
     // ------------------------------------------------------------ G(i-11)
+    // (Layer 1 on the hydraulic group in droplet mode -- it reads layer 0's result only through the R1D ring -- evens the
+    // instruction counts of the two groups, 520 / 310 per row instead of 206 / 599, and was measured 5 % SLOWER:
+    // dispatch_particle 3.32 -> 3.51 ms at 8192^2.)
     // Smoothing reads only the G2 ring, so either group could run it.  The hydraulic group executes
     // 20 % fewer instructions per row than the thermal group, but moving G there was measured 6 %
     // slower (its instruction stream is the latency-heavy one: divisions, sqrt, the TMA wait).
@@ -369,8 +379,6 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             const bool border = (x == 0 || x == W - 1 || (!FREE && (yg == 0 || yg == H - 1)));
             if (owned) {
                 const unsigned idx = off - (unsigned)HGF_LAG_G * pitch;
-                K.dst[0][idx] = border ? rock : sr_;
-                K.dst[1][idx] = border ? dirt : sd_;
                 if (DROPS) {      // smoothing.glsl:77-101 with the momentum map bound: momentum relaxation, display-water decay, H.a
                     float water = c.pf_w;
                     float mx = 0.0f, my = 0.0f, mz = 0.0f, mw = 0.0f;      // the border keeps its terrain; its momentum texel is defined as 0 (oracle: smooth_pass)
@@ -378,22 +386,26 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                         mx = c.pf_m0; my = c.pf_m1; mz = c.pf_m2; mw = c.pf_m3;
                         hg_smooth_momentum(P, mx, my, mz, mw, water);
                     }
-                    K.dst[2][idx] = water;
-                    K.mdst[0][idx] = mx; K.mdst[1][idx] = my; K.mdst[2][idx] = mz; K.mdst[3][idx] = mw;
                     // H.a: the border texel keeps what thermal_transport.glsl:63 left, an interior one gets smoothing.glsl:101: both (r + g) + b
-                    K.total_dst[idx] = (border ? rock : sr_) + (border ? dirt : sd_) + water;
+                    HgF4 h; h.x = border ? rock : sr_; h.y = border ? dirt : sd_; h.z = water; h.w = h.x + h.y + water;
+                    HgF4 m; m.x = mx; m.y = my; m.z = mz; m.w = mw;
+                    K.ha_dst[idx] = h;
+                    K.ma_dst[idx] = m;
+                } else {
+                    K.dst[0][idx] = border ? rock : sr_;
+                    K.dst[1][idx] = border ? dirt : sd_;
                 }
             }
         }
-        // These five planes are not staged through shared memory; fetching the next row's texels now keeps the
-        // global-load latency off the row's critical path (the loads were 2 stall cycles per issued instruction).
+        // The water and momentum texels are not staged through shared memory; fetching the next row's texels now keeps
+        // the global-load latency off the row's critical path (the loads were 2 stall cycles per issued instruction).
         if (DROPS && owned) {
             const int yn = yg + 1;
             if ((FREE || yn >= gy0) && yn < gy1) {
                 const unsigned idn = off - (unsigned)(HGF_LAG_G - 1) * pitch;
-                c.pf_w = HGF_LDG(K.src[2] + idn);
-                c.pf_m0 = HGF_LDG(K.msrc[0] + idn); c.pf_m1 = HGF_LDG(K.msrc[1] + idn);
-                c.pf_m2 = HGF_LDG(K.msrc[2] + idn); c.pf_m3 = HGF_LDG(K.msrc[3] + idn);
+                c.pf_w = HGF_LDG(&K.ha_src[idn].z);
+                const HgF4 m = HGF_LDG4(K.ma_src + idn);
+                c.pf_m0 = m.x; c.pf_m1 = m.y; c.pf_m2 = m.z; c.pf_m3 = m.w;
             }
         }
     }

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) k_rain(SlabDom d, hg_rain_data set, hg_ma
 }  // namespace
 
 int hg_launch_heightmap(hg_ctx* c) {
+    c->p_aos = false;      // droplet mode: the terrain is generated into the planes; everything is overwritten
     SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
     dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
     InitArgs A{};

@@ -66,6 +66,19 @@ struct hg_ctx {
     float* aux;                // HG_NAUX planes (lazy)
     // read index per field group: 0 H, 1 F, 2 V, 3 S (Tex_pair::idx_read)
     int ri[4];
+    // droplet mode: heightmap and momentum map in the reference's TEXTURE layout, one 16-byte texel per cell
+    // ((rock, dirt, water, total), (mx, my, acc_x, acc_y)): four images of plane_elems texels [H set 0, H set 1,
+    // M set 0, M set 1] (lazy).  p_aos: these images, not the planes, hold the current H and M (hg_particle_layout).
+    float4* pa;
+    bool p_aos;
+    // droplet processing order (hg_particles.cu): droplet ids binned by map tile, so the threads of a warp gather from
+    // and scatter to neighbouring texels; rebuilt every p_rebin_period dispatches (HG_DROPS_REBIN, 0 = id order)
+    uint32_t* p_order;         // particle_count ids, or null
+    uint32_t* p_keys;          // bin of every droplet (scratch)
+    uint32_t* p_hist;          // bins + block sums (scratch)
+    int p_bins_cap;
+    int p_rebin_period, p_rebin_age;
+    bool p_order_valid;
     hg_particle* particles;
     uint32_t* lockmap;         // unused by the CUDA path (atomics replace the spin lock); kept for layout parity
 
@@ -146,6 +159,12 @@ static inline float* hg_cur(hg_ctx* c, int plane, int rd) {
 }
 static inline float* hg_total(hg_ctx* c, int rd) { return hg_aux_plane(c, rd ? AX_TOTAL0 + c->ri[0] : AX_TOTAL0 + 1 - c->ri[0]); }
 static inline float* hg_vel(hg_ctx* c, int ch, int rd) { return hg_aux_plane(c, AX_V0 + 4 * (rd ? c->ri[2] : 1 - c->ri[2]) + ch); }
+
+static inline float4* hg_pa_h(hg_ctx* c, int rd) { return c->pa + (size_t)(rd ? c->ri[0] : 1 - c->ri[0]) * c->g.plane_elems; }
+static inline float4* hg_pa_m(hg_ctx* c, int rd) { return c->pa + (size_t)(2 + (rd ? c->ri[2] : 1 - c->ri[2])) * c->g.plane_elems; }
+// Droplet mode keeps H and M either as SoA planes (the PASSES kernels, rain, mass, heightmap init) or as texture-layout
+// images (the droplet kernels and the fused thermal/smoothing tail); converts when the other form is asked for.
+int hg_particle_layout(hg_ctx* c, bool want_aos);
 
 int hg_ensure_aux(hg_ctx* c);
 int hg_fill_total(hg_ctx* c);

@@ -14,22 +14,42 @@
 // applied once per corner, the last-corner-wins quirk of SURVEY.md §8a P2) is carried in
 // registers in corner order 0..3, exactly as the shader re-reads and re-writes its SSBO
 // element.  Order between droplets is free, as it is in the reference.
+//
+// Layout.  Both kernels touch single texels at data-dependent positions, so they work on the heightmap and the
+// momentum map in the reference's own TEXTURE layout, one 16-byte texel per cell ((rock, dirt, water, total) and
+// (mx, my, acc_x, acc_y); hg_particle_layout): the move pass reads (rock, dirt) of a texel with one 8-byte load and a
+// droplet's whole footprint lies in ~11 DRAM sectors instead of 81 with one plane per channel (2.1 KB of DRAM traffic
+// per droplet, profiles/r01i_all_kernels.txt); the erode pass issues one red.global.add.v4.f32 on the heightmap texel
+// and one .v2 on the accumulator half of the momentum texel per corner instead of five scalar reductions.
 #include "hg_internal.cuh"
 
 namespace {
 
 struct PDom { int W, H, pitch; };
 __device__ __forceinline__ size_t pidx(const PDom& d, int x, int y) { return (size_t)(y + HG_HALO_ROWS) * d.pitch + x; }
-__device__ __forceinline__ float fetch(const float* __restrict__ p, const PDom& d, int x, int y) {
-    return (x < 0 || x > d.W - 1 || y < 0 || y > d.H - 1) ? 0.0f : __ldg(p + pidx(d, x, y));
+__device__ __forceinline__ bool poob(const PDom& d, int x, int y) { return x < 0 || x > d.W - 1 || y < 0 || y > d.H - 1; }
+// texelFetch outside the image is 0 (hazard 3)
+__device__ __forceinline__ float2 fetch_xy(const float4* __restrict__ img, const PDom& d, int x, int y) {
+    return poob(d, x, y) ? make_float2(0.0f, 0.0f) : __ldg(reinterpret_cast<const float2*>(img + pidx(d, x, y)));
 }
-// img_bilinear of one channel at a float position (img_interpolation.glsl:3-22)
-__device__ __forceinline__ float bilinear(const float* __restrict__ p, const PDom& d, float sx, float sy) {
+__device__ __forceinline__ float fetch_z(const float4* __restrict__ img, const PDom& d, int x, int y) {
+    return poob(d, x, y) ? 0.0f : __ldg(reinterpret_cast<const float*>(img + pidx(d, x, y)) + 2);
+}
+// img_bilinear (img_interpolation.glsl:3-22) of the first two channels of a texel image at a float position
+__device__ __forceinline__ float2 bilinear_xy(const float4* __restrict__ img, const PDom& d, float sx, float sy) {
     if (!(sx == sx)) sx = 0.0f;
     if (!(sy == sy)) sy = 0.0f;
-    int px = (int)sx, py = (int)sy;
-    float fx = hg_fract(sx), fy = hg_fract(sy);
-    return hg_bilerp(fetch(p, d, px, py), fetch(p, d, px + 1, py), fetch(p, d, px, py + 1), fetch(p, d, px + 1, py + 1), fx, fy);
+    const int px = (int)sx, py = (int)sy;
+    const float fx = hg_fract(sx), fy = hg_fract(sy);
+    const float2 t00 = fetch_xy(img, d, px, py), t10 = fetch_xy(img, d, px + 1, py), t01 = fetch_xy(img, d, px, py + 1), t11 = fetch_xy(img, d, px + 1, py + 1);
+    return make_float2(hg_bilerp(t00.x, t10.x, t01.x, t11.x, fx, fy), hg_bilerp(t00.y, t10.y, t01.y, t11.y, fx, fy));
+}
+__device__ __forceinline__ float bilinear_z(const float4* __restrict__ img, const PDom& d, float sx, float sy) {
+    if (!(sx == sx)) sx = 0.0f;
+    if (!(sy == sy)) sy = 0.0f;
+    const int px = (int)sx, py = (int)sy;
+    const float fx = hg_fract(sx), fy = hg_fract(sy);
+    return hg_bilerp(fetch_z(img, d, px, py), fetch_z(img, d, px + 1, py), fetch_z(img, d, px, py + 1), fetch_z(img, d, px + 1, py + 1), fx, fy);
 }
 
 // rand(vec2), particle.glsl:41-44
@@ -37,13 +57,14 @@ __device__ __forceinline__ float prand(float px, float py) {
     return hg_fract(1e4f * hg_sinf(17.0f * px + py * 0.1f) * (0.1f + fabsf(hg_sinf(py * 13.0f + px))));
 }
 
-struct MoveArgs { const float *rock, *dirt, *water, *mx, *my; hg_particle* particles; };
+struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t* order; };
 
 // particle.glsl:64-136
 __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, hg_erosion_data set, hg_map_settings_data map_set,
                                                        MoveArgs A, uint32_t count, float time, int should_rain) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
+    if (A.order) id = A.order[id];      // thread k takes the k-th droplet in tile order; the droplet keeps its id (spawn hash)
     hg_particle p = A.particles[id];
     if (p.iters == 0 && !should_rain) return;
 #pragma unroll
@@ -64,19 +85,17 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
         }
     }
     float px = p.position[0], py = p.position[1];
-    // get_terr_normal, particle.glsl:50-62 (bilinear samples)
-    float rr = bilinear(A.rock, d, px + 1.0f, py + 0.0f), rg = bilinear(A.dirt, d, px + 1.0f, py + 0.0f);
-    float lr = bilinear(A.rock, d, px + -1.0f, py + 0.0f), lg = bilinear(A.dirt, d, px + -1.0f, py + 0.0f);
-    float br = bilinear(A.rock, d, px + 0.0f, py + -1.0f), bg = bilinear(A.dirt, d, px + 0.0f, py + -1.0f);
-    float tr = bilinear(A.rock, d, px + 0.0f, py + 1.0f), tg = bilinear(A.dirt, d, px + 0.0f, py + 1.0f);
-    float dx = (rr + rg - lr - lg);
-    float dz = (tr + tg - br - bg);
+    // get_terr_normal, particle.glsl:50-62 (bilinear samples of rock and dirt)
+    const float2 r_ = bilinear_xy(A.ha, d, px + 1.0f, py + 0.0f), l_ = bilinear_xy(A.ha, d, px + -1.0f, py + 0.0f);
+    const float2 b_ = bilinear_xy(A.ha, d, px + 0.0f, py + -1.0f), t_ = bilinear_xy(A.ha, d, px + 0.0f, py + 1.0f);
+    float dx = (r_.x + r_.y - l_.x - l_.y);
+    float dz = (t_.x + t_.y - b_.x - b_.y);
     float nx = dx * 2.0f - 0.0f * dz, ny = 0.0f * 0.0f - 2.0f * 2.0f, nz = 2.0f * dz - dx * 0.0f;
     float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
     nx *= inv; ny *= inv; nz *= inv;
-    float momx = bilinear(A.mx, d, px, py), momy = bilinear(A.my, d, px, py);
-    float water = bilinear(A.water, d, px, py);
-
+    const float2 mom = bilinear_xy(A.ma, d, px, py);
+    const float momx = mom.x, momy = mom.y;
+    float water = bilinear_z(A.ha, d, px, py);
     p.velocity[0] -= (set.d_t * nx) / (p.volume) * set.G;
     p.velocity[1] -= (set.d_t * nz) / (p.volume) * set.G;
     float lm = sqrtf(momx * momx + momy * momy), lv = sqrtf(p.velocity[0] * p.velocity[0] + p.velocity[1] * p.velocity[1]);
@@ -115,27 +134,29 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
     A.particles[id] = p;
 }
 
-struct ErodePlanes { float *rock, *dirt, *water, *mz, *mw; };
+struct ErodeImages { float4 *ha, *ma; };
 
 // What one corner of one droplet adds to its texel (particle_erosion.glsl:61-75,94-98): deposits per layer
 // (only where the layer deposited), display water and the momentum accumulator.
-struct CornerAdd { float rock, dirt, water, mz, mw; bool has_rock, has_dirt; };
+struct CornerAdd { float rock, dirt, water, mz, mw; };
+
+// (rock, dirt, water, -) += on the heightmap texel and (acc_x, acc_y) += on the momentum texel: two vector reductions.
+// A layer without a deposit adds +0.0f, which leaves every value as it is.
+__device__ __forceinline__ void texel_add(const ErodeImages& A, size_t ti, float rock, float dirt, float water, float mz, float mw) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(A.ha + ti), "f"(rock), "f"(dirt), "f"(water), "f"(0.0f) : "memory");
+    asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(reinterpret_cast<float*>(A.ma + ti) + 2), "f"(mz), "f"(mw) : "memory");
+}
 
 // Apply the corner additions of all 32 lanes.  Lanes of the warp that hit the same texel are found with ONE
-// match per corner; the lowest such lane sums its peers' five values in lane order (a lane that has no deposit
-// for a layer contributes its 0.0f, which changes no sum) and issues one red per plane.  All 32 lanes must call.
-__device__ __forceinline__ void warp_corner_add(const ErodePlanes& A, size_t ti, const CornerAdd& v, bool act) {
+// match per corner; the lowest such lane sums its peers' five values in lane order and issues the two reductions.
+// All 32 lanes must call.
+__device__ __forceinline__ void warp_corner_add(const ErodeImages& A, size_t ti, const CornerAdd& v, bool act) {
     const int lane = threadIdx.x & 31;
     unsigned long long key = act ? (unsigned long long)ti : ~0ull - lane;
     unsigned peers = __match_any_sync(0xffffffffu, key);
-    unsigned rock_lanes = __ballot_sync(0xffffffffu, act && v.has_rock), dirt_lanes = __ballot_sync(0xffffffffu, act && v.has_dirt);
     if (!act) return;
     if (__popc(peers) == 1) {              // the common case on a sparse map: nobody else in the warp hits this texel
-        if (v.has_dirt) atomicAdd(A.dirt + ti, v.dirt);
-        if (v.has_rock) atomicAdd(A.rock + ti, v.rock);
-        atomicAdd(A.water + ti, v.water);
-        atomicAdd(A.mz + ti, v.mz);
-        atomicAdd(A.mw + ti, v.mw);
+        texel_add(A, ti, v.rock, v.dirt, v.water, v.mz, v.mw);
         return;
     }
     // peers > 1 only occurs among active lanes (inactive keys are unique)
@@ -150,13 +171,7 @@ __device__ __forceinline__ void warp_corner_add(const ErodePlanes& A, size_t ti,
         s_mz += __shfl_sync(peers, v.mz, src);
         s_mw += __shfl_sync(peers, v.mw, src);
     }
-    if (lane == __ffs(peers) - 1) {
-        if (dirt_lanes & peers) atomicAdd(A.dirt + ti, s_dirt);
-        if (rock_lanes & peers) atomicAdd(A.rock + ti, s_rock);
-        atomicAdd(A.water + ti, s_water);
-        atomicAdd(A.mz + ti, s_mz);
-        atomicAdd(A.mw + ti, s_mw);
-    }
+    if (lane == __ffs(peers) - 1) texel_add(A, ti, s_rock, s_dirt, s_water, s_mz, s_mw);
 }
 
 // terr -= eroded with the exhausted-layer clamp of particle_erosion.glsl:53-59, as one
@@ -176,12 +191,52 @@ __device__ __forceinline__ float erode_clamped(float* addr, float eroded, float*
     return __uint_as_float(assumed);
 }
 
-struct ErodeArgs : ErodePlanes { hg_particle* particles; };
+// erode_clamped for all 32 lanes at once (all must call; `on`: the lane erodes).  Lanes of the warp that erode the same
+// layer of the same texel -- the normal case once the droplets are processed in tile order -- are applied in lane order
+// by ONE compare-and-swap of their leader instead of up to 32 competing ones: every lane replays the sequence
+// (running = max(running - eroded_j, 0), what erode_clamped stores) from the value the leader read, which gives each
+// its own value before and unclamped value after, exactly as if the lanes had taken the reference's lock one after
+// the other; the leader publishes the final value and the group repeats if another warp got in between.
+__device__ __forceinline__ void warp_erode(float* addr, float eroded, bool on, float* old_terr, float* after) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long key = on ? (unsigned long long)addr : (unsigned long long)lane;      // an address is never < 32
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (!on) return;
+    if (__popc(peers) == 1) {
+        *old_terr = erode_clamped(addr, eroded, after);
+        return;
+    }
+    const int leader = __ffs(peers) - 1;
+    unsigned* const ua = reinterpret_cast<unsigned*>(addr);
+    unsigned cur = 0;
+    if (lane == leader) cur = *reinterpret_cast<volatile unsigned*>(ua);
+    for (;;) {
+        cur = __shfl_sync(peers, cur, leader);
+        float running = __uint_as_float(cur), mine_old = 0.0f, mine_after = 0.0f;
+        unsigned rest = peers;
+        while (rest) {
+            const int src = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const float e = __shfl_sync(peers, eroded, src);
+            const float nv = running - e;
+            if (src == lane) { mine_old = running; mine_after = nv; }
+            running = (nv < 0.0f) ? 0.0f : nv;
+        }
+        unsigned seen = cur;
+        if (lane == leader) seen = atomicCAS(ua, cur, __float_as_uint(running));
+        seen = __shfl_sync(peers, seen, leader);
+        if (seen == cur) { *old_terr = mine_old; *after = mine_after; return; }
+        cur = seen;
+    }
+}
+
+struct ErodeArgs : ErodeImages { hg_particle* particles; const uint32_t* order; };
 
 // particle_erosion.glsl:101-128 + erode_layers :22-85
 __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, ErodeArgs A, uint32_t count) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = id < count;
+    if (live && A.order) id = A.order[id];
     hg_particle part = {};
     if (live) part = A.particles[id];
     live = live && part.iters != 0;
@@ -205,44 +260,48 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
         size_t ti = act ? pidx(d, cx, cy) : 0;
         float multipl = wx * wy;
         float dep[2] = {0.0f, 0.0f};      // value-independent additions to terrain, per layer
-        bool has_dep[2] = {false, false};
-        if (act) {
-            float cap = 0.0f;
+        // erode_layers (particle_erosion.glsl:22-85) layer by layer with every lane of the warp in step, because the
+        // erosion of a layer is a warp-collective update (warp_erode); `open`: the lane is still inside the shader's loop
+        float cap = 0.0f;
+        bool open = act;
 #pragma unroll
-            for (int i = HG_SED_LAYERS - 1; i >= 0; i--) {
-                if (part.to_kill) {
-                    float sed = old_sed[i] * multipl;
-                    dep[i] = sed; has_dep[i] = true;
-                    part.sediment[i] -= sed;
-                    continue;
-                }
-                float c = hg_max(0.0f, part.sc - cap);
-                float s1 = old_sed[i];
-                if (c > s1) {
-                    float eroded = multipl * P.Kls[i] * (c - s1);
-                    s1 += eroded;
-                    float after;
-                    float old_terr = erode_clamped((i == 0 ? A.rock : A.dirt) + ti, eroded, &after);
-                    if (after < 0.0f) {
-                        s1 += after;
-                        cap += old_terr;
-                    } else {
-                        part.sediment[i] = s1;
-                        break;
-                    }
+        for (int i = HG_SED_LAYERS - 1; i >= 0; i--) {
+            const bool kill = open && part.to_kill;
+            if (kill) {
+                float sed = old_sed[i] * multipl;
+                dep[i] = sed;
+                part.sediment[i] -= sed;
+            }
+            const float c = hg_max(0.0f, part.sc - cap);
+            float s1 = old_sed[i];
+            const bool erode = open && !kill && c > s1;
+            const float eroded = erode ? multipl * P.Kls[i] * (c - s1) : 0.0f;
+            float old_terr = 0.0f, after = 0.0f;
+            warp_erode(reinterpret_cast<float*>(A.ha + ti) + i, eroded, erode, &old_terr, &after);      // .x rock, .y dirt
+            if (erode) {
+                s1 += eroded;
+                if (after < 0.0f) {
+                    s1 += after;
+                    cap += old_terr;
+                    part.sediment[i] = s1;
                 } else {
-                    float deposit = multipl * P.Kld[i] * (s1 - c);
-                    s1 -= deposit;
-                    dep[i] = deposit; has_dep[i] = true;
+                    part.sediment[i] = s1;
+                    open = false;      // break
                 }
+            } else if (open && !kill) {
+                float deposit = multipl * P.Kld[i] * (s1 - c);
+                s1 -= deposit;
+                dep[i] = deposit;
                 part.sediment[i] = s1;
             }
+        }
+        if (act) {
             float conv = part.sediment[0] * P.Kconv * P.d_t;
             part.sediment[1] += conv;
             part.sediment[0] -= conv;
         }
         CornerAdd v;
-        v.rock = dep[0]; v.dirt = dep[1]; v.has_rock = has_dep[0]; v.has_dirt = has_dep[1];
+        v.rock = dep[0]; v.dirt = dep[1];
         v.water = 1e-5f * part.volume * multipl;
         v.mz = part.volume * part.velocity[0] * multipl;
         v.mw = part.volume * part.velocity[1] * multipl;
@@ -251,13 +310,126 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
     if (live) A.particles[id] = part;
 }
 
+
+// ------------------------------------------------------------------ processing order
+// Droplets are spawned at hashed positions, so droplet k and droplet k+1 sit in unrelated parts of the map and every
+// thread of a warp gathers from and scatters to its own DRAM sectors (66 % of the DRAM peak at 7 % issue utilisation,
+// profiles/r01i_all_kernels.txt).  The order in which droplets are processed is free (the reference leaves it to the
+// GPU's scheduling and to its lock), so both kernels take their droplet from an index array sorted by map tile: a
+// counting sort over the tiles of the droplets' positions (tile = 2^shift cells, at most 2^21 bins: single cells
+// when hmap_dims is small, so that the droplets of one texel sit next to each other and the warp-level combining of
+// the erode pass meets them).  Droplets move at most 0.25 cell per step and about 1 % respawn per step, so the order
+// is rebuilt only every p_rebin_period dispatches.
+constexpr int kScanBlock = 2048;      // bins per scan block (512 threads x 4)
+struct BinDom { int shift, bx, by; };
+__global__ void __launch_bounds__(256) k_bin_keys(const hg_particle* parts, uint32_t count, BinDom b, uint32_t* keys, uint32_t* hist) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const float2 pos = *reinterpret_cast<const float2*>(parts[id].position);
+    int cx = (int)fminf(fmaxf(pos.x, 0.0f), 1e9f) >> b.shift, cy = (int)fminf(fmaxf(pos.y, 0.0f), 1e9f) >> b.shift;
+    cx = min(cx, b.bx - 1); cy = min(cy, b.by - 1);
+    const uint32_t key = (uint32_t)cy * (uint32_t)b.bx + (uint32_t)cx;
+    keys[id] = key;
+    atomicAdd(hist + key, 1u);
+}
+// exclusive scan of every block of kScanBlock bins in place; block totals to sums[]
+__global__ void __launch_bounds__(512) k_bin_scan1(uint32_t* hist, int nbins, uint32_t* sums) {
+    __shared__ uint32_t wsum[16];
+    const int base = blockIdx.x * kScanBlock + threadIdx.x * 4;
+    uint32_t v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < nbins ? hist[base + k] : 0u; t += v[k]; }
+    uint32_t incl = t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < 16 ? wsum[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += n; }
+        if (lane < 16) wsum[lane] = wi - w;
+        if (lane == 15) sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + incl - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < nbins) hist[base + k] = run; run += v[k]; }
+}
+// exclusive scan of the block totals (at most 1024), one block
+__global__ void __launch_bounds__(1024) k_bin_scan2(uint32_t* sums, int n) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = (int)threadIdx.x < n ? sums[threadIdx.x] : 0u, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t m = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += m; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t m = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += m; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < n) sums[threadIdx.x] = wsum[warp] + incl - v;
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* keys, uint32_t count, uint32_t* hist, const uint32_t* sums, uint32_t* order) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const uint32_t key = keys[id];
+    const uint32_t pos = atomicAdd(hist + key, 1u) + sums[key / kScanBlock];
+    order[pos] = id;
+}
+
 }  // namespace
+
+// (Re)build the processing order from the droplets' current positions.
+static int rebuild_order(hg_ctx* c, uint32_t count) {
+    int hx = c->map.hmap_dims[0] > 0 ? c->map.hmap_dims[0] : c->g.W, hy = c->map.hmap_dims[1] > 0 ? c->map.hmap_dims[1] : c->g.H;
+    if (hx > c->g.W) hx = c->g.W;
+    if (hy > c->g.H) hy = c->g.H;
+    BinDom b{0, hx, hy};
+    while ((long long)b.bx * b.by > (1LL << 21)) { b.shift++; b.bx = (hx + (1 << b.shift) - 1) >> b.shift; b.by = (hy + (1 << b.shift) - 1) >> b.shift; }
+    const int nbins = b.bx * b.by, nblocks = (nbins + kScanBlock - 1) / kScanBlock;
+    if (!c->p_order) {
+        HG_CUDA(cudaMalloc(&c->p_order, (size_t)c->particle_count * sizeof(uint32_t)));
+        HG_CUDA(cudaMalloc(&c->p_keys, (size_t)c->particle_count * sizeof(uint32_t)));
+    }
+    if (c->p_bins_cap < nbins) {
+        if (c->p_hist) HG_CUDA(cudaFree(c->p_hist));
+        HG_CUDA(cudaMalloc(&c->p_hist, ((size_t)nbins + 1024) * sizeof(uint32_t)));
+        c->p_bins_cap = nbins;
+    }
+    uint32_t* sums = c->p_hist + nbins;
+    HG_CUDA(cudaMemsetAsync(c->p_hist, 0, (size_t)nbins * sizeof(uint32_t), c->stream));
+    k_bin_keys<<<(count + 255) / 256, 256, 0, c->stream>>>(c->particles, count, b, c->p_keys, c->p_hist);
+    HG_LAUNCH_CHECK(c);
+    k_bin_scan1<<<nblocks, 512, 0, c->stream>>>(c->p_hist, nbins, sums);
+    HG_LAUNCH_CHECK(c);
+    k_bin_scan2<<<1, 1024, 0, c->stream>>>(sums, nblocks);
+    HG_LAUNCH_CHECK(c);
+    k_bin_scatter<<<(count + 255) / 256, 256, 0, c->stream>>>(c->p_keys, count, c->p_hist, sums, c->p_order);
+    HG_LAUNCH_CHECK(c);
+    c->p_order_valid = true;
+    c->p_rebin_age = 0;
+    return HG_OK;
+}
 
 int hg_launch_particle_move(hg_ctx* c, float time, int should_rain) {
     PDom d{c->g.W, c->g.H, c->g.pitch};
     uint32_t count = (c->particle_count / 64u) * 64u;    // glDispatchCompute(particle_count/64), erosion.cpp:127
     if (!count) return HG_OK;
-    MoveArgs A{hg_cur(c, PL_ROCK, 1), hg_cur(c, PL_DIRT, 1), hg_cur(c, PL_WATER, 1), hg_vel(c, 0, 1), hg_vel(c, 1, 1), c->particles};
+    int rc = hg_particle_layout(c, true);
+    if (rc) return rc;
+    // processing order: rebuilt when it has aged; a fresh context (nothing spawned yet) moves in id order and sorts
+    // after the move, when the droplets have their spawn positions (hg_launch_particle_erode)
+    if (c->p_rebin_period > 0 && c->p_order_valid && ++c->p_rebin_age >= c->p_rebin_period) {
+        rc = rebuild_order(c, count);
+        if (rc) return rc;
+    }
+    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, c->p_order_valid ? c->p_order : nullptr};
     k_particle_move<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, c->erosion, c->map, A, count, time, should_rain);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
@@ -268,9 +440,14 @@ int hg_launch_particle_erode(hg_ctx* c) {
     uint32_t count = (c->particle_count / 64u) * 64u;
     if (!count) return HG_OK;
     // in place on the READ images of heightmap and momentum map (erosion.cpp:141-143)
+    int rc = hg_particle_layout(c, true);
+    if (rc) return rc;
+    if (c->p_rebin_period > 0 && !c->p_order_valid) {
+        rc = rebuild_order(c, count);
+        if (rc) return rc;
+    }
     ErodeArgs A;
-    A.rock = hg_cur(c, PL_ROCK, 1); A.dirt = hg_cur(c, PL_DIRT, 1); A.water = hg_cur(c, PL_WATER, 1);
-    A.mz = hg_vel(c, 2, 1); A.mw = hg_vel(c, 3, 1); A.particles = c->particles;
+    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = c->p_order_valid ? c->p_order : nullptr;
     k_particle_erode<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count);
     HG_LAUNCH_CHECK(c);
     return HG_OK;

@@ -185,6 +185,8 @@ static int require_full_map(hg_ctx* c) {
 int hg_launch_pass(hg_ctx* c, int pass) {
     int rc = require_full_map(c);
     if (rc) return rc;
+    rc = hg_particle_layout(c, false);      // the 1:1 pass kernels work on the planes
+    if (rc) return rc;
     Dom d{c->g.W, c->g.H, c->g.pitch};
     dim3 b(32, 8), g = grid_for(c, b);
     switch (pass) {
