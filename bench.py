@@ -353,6 +353,21 @@ def droplet_config(rig, steps=40, warm=20):
     return out
 
 
+def contracted_build(args):
+    """The same headline workload on the opt-in CONTRACTED build of the library (HG_FMAD=1: -fmad=true, results within
+    the north star's tolerance of the reference instead of bit-identical; tests/test_fmad_build.py), in a child process:
+    what bit-exactness costs.  The headline numbers of this line are the default, bit-exact library's."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(args.steps), "--warmup", str(args.warmup), "--no-extras", "--no-cpu-baseline", "--e2e-steps", "0"]
+    try:
+        res = subprocess.run(cmd, env=dict(os.environ, HG_FMAD="1"), capture_output=True, text=True, timeout=600)
+        js = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+        return {"what": "libhydrogen_b200_fmad.so (-fmad=true), same workload, same timing; parity: <= 1e-5 per field after one step, not bit-identical",
+                "value": js["value"], "unit": js["unit"], "ms_per_step": js["ms_per_step"], "kernel_ms": js["roofline"]["kernel_ms"],
+                "roofline_frac": js["roofline"]["frac"], "clocks": js["clocks"]}
+    except Exception as e:      # the headline must not depend on it
+        return {"error": repr(e)[:300]}
+
+
 def slab_parity(rig, W=1024, rows=512, steps=48):
     """scripts/mgpu_check.py inside the bench: every rank steps its slab of a W x (rows * N) map with NVLink halo
     pushes (CUDA IPC between the processes) AND the whole map on its own GPU, and compares its rows bit for bit;
@@ -499,6 +514,8 @@ def main():
                 rig.barrier()
                 line["cfg5_65536"] = e5
 
+    if rank == 0 and n == 1 and not args.no_extras and default_shape and os.environ.get("HG_FMAD") != "1":
+        line["contracted_build"] = contracted_build(args)
     if rank == 0:
         if n == 1 and not args.no_cpu_baseline:
             got = cpu_reference(512, 150)        # ~10-20 s of CPU work

@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("HG_B200_LIB") or os.path.join(_HERE, "libhydrogen_b200.so")      # HG_B200_LIB: another build of the same library (tuning aid)
+# HG_FMAD=1: the opt-in contracted build (-fmad=true; within the north star's tolerance of the reference instead of
+# bit-identical, tests/test_fmad_build.py).  HG_B200_LIB: any other build of the same library (tuning aid).
+LIB_PATH = os.environ.get("HG_B200_LIB") or os.path.join(_HERE, "libhydrogen_b200_fmad.so" if os.environ.get("HG_FMAD") == "1" else "libhydrogen_b200.so")
 
 HG_OK, HG_ERR_INVALID, HG_ERR_CUDA, HG_ERR_STATE, HG_ERR_NO_DEVICE = range(5)
 HG_GRID, HG_PARTICLES = 0, 1
@@ -109,6 +111,8 @@ SYMBOLS = {
     "hg_slab_refresh_halo": (_i, [_vp]),
     "hg_register_gl": (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "hg_publish_gl": (_i, [_vp, _i]),
+    "hg_unregister_gl": (_i, [_vp]),
+    "hg_pack_device": (_i, [_vp, _i, _vp]),
 }
 
 _lib = None

@@ -196,6 +196,10 @@ class Context:
     def slab_errors(self):
         v = C.c_uint64(); check(self.L.hg_slab_errors(self.h, C.byref(v))); return v.value
 
+    def pack_device(self, field, device_ptr):
+        """hg_pack_device: the field as an RGBA32F image in device memory (rows*W*4 floats at device_ptr), asynchronous"""
+        check(self.L.hg_pack_device(self.h, int(field), C.c_void_p(int(device_ptr))))
+
     def refresh_halo(self):
         """hg_slab_refresh_halo: collective re-fill of the ghost rows after uploads on a connected slab"""
         check(self.L.hg_slab_refresh_halo(self.h))

@@ -17,13 +17,18 @@ void hg_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* hg_last_error(void) { return g_err; }
-extern "C" const char* hg_version(void) { return "hydrogen_b200 0.1 sm_100a"; }
+#ifdef HG_CONTRACTED
+extern "C" const char* hg_version(void) { return "hydrogen_b200 0.2 sm_100a contracted (-fmad=true: within tolerance of the reference, not bit-identical)"; }
+#else
+extern "C" const char* hg_version(void) { return "hydrogen_b200 0.2 sm_100a"; }
+#endif
 
 // ------------------------------------------------------------------ lifetime
 
 static void free_ctx(hg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    hg_unregister_gl(c);
     hg_slab_disconnect(c);
     if (c->arena) cudaFree(c->arena);
     if (c->aux) cudaFree(c->aux);
@@ -687,13 +692,97 @@ extern "C" int hg_run_profiled(hg_ctx* c, uint32_t n_steps, float time0, float d
 extern "C" int hg_get_steps(hg_ctx* c, uint32_t* s) { HG_CHECK_CTX(c); if (!s) return HG_ERR_INVALID; *s = c->erosion_steps; return HG_OK; }
 extern "C" int hg_set_steps(hg_ctx* c, uint32_t s) { HG_CHECK_CTX(c); c->erosion_steps = s; return HG_OK; }
 
-#ifndef HG_WITH_GL
+// ------------------------------------------------------------- publishing to a renderer
+// The only consumer of the fields in the reference is its renderer, which samples the READ textures of the heightmap
+// and sediment pairs (src/rendering.cpp:103-104; gl::Tex_pair read index, src/shaderprogram.cpp:51-82).  Two steps:
+// (1) pack a field into a linear DEVICE image in the reference's texture format -- RGBA32F, [row][x][4], H.a
+//     included -- which is all that any interop (GL, Vulkan/EGL external memory, a CUDA renderer) needs and is what
+//     the tests check against hg_download; (2) with -DHG_WITH_GL, copy that image into the mapped GL texture.
+extern "C" int hg_pack_device(hg_ctx* c, int field, float* dst_rgba32f_device) {
+    HG_CHECK_CTX(c);
+    if (!dst_rgba32f_device) { hg_set_error("null device image"); return HG_ERR_INVALID; }
+    const size_t n = (size_t)c->g.rows * c->g.W;
+    if (c->p_aos && (field == HG_FIELD_HEIGHTMAP || field == HG_FIELD_VELOCITY)) {      // droplet mode: already in texture layout
+        const float4* img = (field == HG_FIELD_HEIGHTMAP ? hg_pa_h(c, 1) : hg_pa_m(c, 1)) + (size_t)HG_HALO_ROWS * c->g.pitch;
+        HG_CUDA(cudaMemcpyAsync(dst_rgba32f_device, img, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        return HG_OK;
+    }
+    Chan4 ch; int synth;
+    int rc = field_channels(c, field, &ch, &synth, false);
+    if (rc) return rc;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_pack<<<blocks, 256, 0, c->stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<float4*>(dst_rgba32f_device), synth);
+    HG_LAUNCH_CHECK(c);
+    return HG_OK;
+}
+
+#ifdef HG_WITH_GL
+#include <cuda_gl_interop.h>
+// gl_res[pair][index]: pair 0 = heightmap, 1 = sediment; index = the texture's place in its gl::Tex_pair
+static int gl_publish_one(hg_ctx* c, int field, cudaGraphicsResource_t res) {
+    int rc = hg_pack_device(c, field, c->gl_stage);
+    if (rc) return rc;
+    HG_CUDA(cudaGraphicsMapResources(1, &res, c->stream));
+    cudaArray_t arr = nullptr;
+    cudaError_t e = cudaGraphicsSubResourceGetMappedArray(&arr, res, 0, 0);
+    if (e == cudaSuccess)      // a slab publishes its rows at its place in the map-sized texture
+        e = cudaMemcpy2DToArrayAsync(arr, 0, (size_t)c->g.row0, c->gl_stage, (size_t)c->g.W * 4 * sizeof(float),
+                                     (size_t)c->g.W * 4 * sizeof(float), (size_t)c->g.rows, cudaMemcpyDeviceToDevice, c->stream);
+    cudaError_t e2 = cudaGraphicsUnmapResources(1, &res, c->stream);
+    if (e != cudaSuccess || e2 != cudaSuccess) { hg_set_error("publishing to the GL texture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2)); return HG_ERR_CUDA; }
+    return HG_OK;
+}
+
+extern "C" int hg_register_gl(hg_ctx* c, const unsigned heightmap_tex[2], const unsigned sediment_tex[2]) {
+    HG_CHECK_CTX(c);
+    if (!heightmap_tex || !sediment_tex) { hg_set_error("null texture names"); return HG_ERR_INVALID; }
+    hg_unregister_gl(c);
+    const unsigned* names[2] = {heightmap_tex, sediment_tex};
+    for (int p = 0; p < 2; p++)
+        for (int k = 0; k < 2; k++) {
+            cudaGraphicsResource_t r = nullptr;
+            // RGBA32F GL_TEXTURE_2D of the map's size (gl::gen_texture, src/shaderprogram.cpp:14-33); CUDA only writes it
+            cudaError_t e = cudaGraphicsGLRegisterImage(&r, (GLuint)names[p][k], GL_TEXTURE_2D, cudaGraphicsRegisterFlagsWriteDiscard);
+            if (e != cudaSuccess) {
+                hg_set_error("cudaGraphicsGLRegisterImage(texture %u) failed: %s (is the GL context current on this thread, on device %d?)", names[p][k], cudaGetErrorString(e), c->device);
+                hg_unregister_gl(c);
+                return HG_ERR_CUDA;
+            }
+            c->gl_res[p][k] = r;
+        }
+    HG_CUDA(cudaMalloc(&c->gl_stage, (size_t)c->g.rows * c->g.W * 4 * sizeof(float)));
+    return HG_OK;
+}
+
+extern "C" int hg_unregister_gl(hg_ctx* c) {
+    if (!c) return HG_ERR_INVALID;
+    for (int p = 0; p < 2; p++)
+        for (int k = 0; k < 2; k++)
+            if (c->gl_res[p][k]) { cudaGraphicsUnregisterResource(static_cast<cudaGraphicsResource_t>(c->gl_res[p][k])); c->gl_res[p][k] = nullptr; }
+    if (c->gl_stage) { cudaFree(c->gl_stage); c->gl_stage = nullptr; }
+    return HG_OK;
+}
+
+// read_index: bit 0 = index of the heightmap texture the renderer will sample (Tex_pair::get_read_tex of
+// State::World::Textures::heightmap), bit 1 = the same for the sediment pair.  Asynchronous on the handle's stream;
+// GL may sample the textures once the stream has been synchronised (hg_sync) -- the reference's own frame does the
+// equivalent with glMemoryBarrier between its dispatches and its draw (src/erosion.cpp:99).
+extern "C" int hg_publish_gl(hg_ctx* c, int read_index) {
+    HG_CHECK_CTX(c);
+    if (!c->gl_stage) { hg_set_error("hg_publish_gl before hg_register_gl"); return HG_ERR_STATE; }
+    int rc = gl_publish_one(c, HG_FIELD_HEIGHTMAP, static_cast<cudaGraphicsResource_t>(c->gl_res[0][read_index & 1]));
+    if (rc) return rc;
+    if (c->erosion_type == HG_PARTICLES) return HG_OK;      // the droplet mode keeps no suspended sediment field
+    return gl_publish_one(c, HG_FIELD_SEDIMENT, static_cast<cudaGraphicsResource_t>(c->gl_res[1][(read_index >> 1) & 1]));
+}
+#else
 extern "C" int hg_register_gl(hg_ctx*, const unsigned[2], const unsigned[2]) {
-    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image)");
+    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image); hg_pack_device gives the same RGBA32F image in device memory");
     return HG_ERR_STATE;
 }
+extern "C" int hg_unregister_gl(hg_ctx*) { return HG_OK; }
 extern "C" int hg_publish_gl(hg_ctx*, int) {
-    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image)");
+    hg_set_error("built without HG_WITH_GL (no OpenGL in the build image); hg_pack_device gives the same RGBA32F image in device memory");
     return HG_ERR_STATE;
 }
 #endif

@@ -110,6 +110,10 @@ struct hg_ctx {
     cudaEvent_t ev_up, ev_comp, ev_packed, ev_down;
     bool host_pipe_busy;       // ev_packed / ev_down have been recorded at least once
 
+    // CUDA-GL interop (HG_WITH_GL): registered textures [heightmap | sediment][index in the Tex_pair], staging image
+    void* gl_res[2][2];
+    float* gl_stage;
+
     // multi-GPU slabs (hg_slab.cu): every rank's arena, ordered by row0
     HgSlabTable slabs;
     bool slab_ipc[HG_MAX_SLABS];

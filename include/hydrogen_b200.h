@@ -204,10 +204,24 @@ int hg_slab_errors(hg_ctx* ctx, uint64_t* count);
  * itself on a connected slab (so loading is collective too).  No-op on an unconnected context. */
 int hg_slab_refresh_halo(hg_ctx* ctx);
 
-/* ---- optional CUDA-GL interop with the reference renderer (src/rendering.cpp:104-105).
- * Compiled only with -DHG_WITH_GL (no GL in the build image); otherwise HG_ERR_STATE. ---- */
+/* ---- publishing the fields to a renderer.  The reference's only consumer of the fields is its renderer,
+ * which samples the READ textures of the heightmap and sediment pairs (src/rendering.cpp:103-104,
+ * gl::Tex_pair::get_read_tex, src/shaderprogram.cpp:51-82).
+ *
+ * hg_pack_device: the field as a linear image in DEVICE memory in the reference's texture format (RGBA32F,
+ * [row][x][4], rows*map_w*4 floats, H.a included): what hg_publish_gl copies into the GL texture, and the
+ * entry for any other interop (external memory, a CUDA renderer).  Asynchronous on the handle's stream.
+ *
+ * hg_register_gl / hg_publish_gl / hg_unregister_gl: CUDA-GL interop with the reference's own textures, compiled
+ * with -DHG_WITH_GL (cudaGraphicsGLRegisterImage on the four RGBA32F GL_TEXTURE_2D names of the two pairs; the GL
+ * context must be current on the calling thread and live on the handle's device).  read_index: bit 0 = index
+ * inside the heightmap pair of the texture the renderer samples next, bit 1 = the same for the sediment pair.
+ * A slab publishes its rows at their place.  Without HG_WITH_GL (this image has no OpenGL) they return
+ * HG_ERR_STATE. ---- */
+int hg_pack_device(hg_ctx* ctx, int field, float* dst_rgba32f_device);
 int hg_register_gl(hg_ctx* ctx, const unsigned heightmap_tex[2], const unsigned sediment_tex[2]);
 int hg_publish_gl(hg_ctx* ctx, int read_index);
+int hg_unregister_gl(hg_ctx* ctx);
 
 #ifdef __cplusplus
 }

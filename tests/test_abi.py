@@ -62,3 +62,28 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(import|from)\s+oracle\b|hg_oracle|oracle/", t, flags=re.M):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_gl_interop_path_compiles(tmp_path):
+    """hg_register_gl / hg_publish_gl / hg_unregister_gl: no OpenGL exists in this image, so the
+    -DHG_WITH_GL path cannot run; it must at least compile and reference the CUDA-GL interop calls it is built on.
+    include/gl_stub/GL/gl.h is a three-typedef stand-in for <GL/gl.h> (a real build never sees it)."""
+    obj = tmp_path / "ctx_gl.o"
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-DHG_WITH_GL",
+                    "-I", os.path.join(ROOT, "include", "gl_stub"), "-c", os.path.join(ROOT, "hydro_gen_b200", "csrc", "hg_context.cu"),
+                    "-o", str(obj)], check=True, capture_output=True)
+    syms = subprocess.run(["nm", str(obj)], check=True, capture_output=True, text=True).stdout
+    for name in ("cudaGraphicsGLRegisterImage", "cudaGraphicsMapResources", "cudaGraphicsSubResourceGetMappedArray",
+                 "cudaMemcpy2DToArrayAsync", "cudaGraphicsUnmapResources", "cudaGraphicsUnregisterResource"):
+        assert re.search(rf"\bU {name}\b", syms), f"{name} is not used by the HG_WITH_GL build"
+    for name in ("hg_register_gl", "hg_publish_gl", "hg_unregister_gl", "hg_pack_device"):
+        assert re.search(rf"\bT {name}\b", syms), name
+
+
+def test_gl_entry_points_fail_loudly_without_gl(built):
+    """the shipped library is built without HG_WITH_GL: the entry points exist and say why they cannot work"""
+    import ctypes as C
+    arr = (C.c_uint * 2)(1, 2)
+    assert built.hg_register_gl(None, arr, arr) != 0
+    assert b"HG_WITH_GL" in built.hg_last_error()
+    assert built.hg_publish_gl(None, 0) != 0

@@ -350,3 +350,33 @@ def test_balanced_partition_large_slab_bit_exact(built):
     _compare(ctx, ref, ("heightmap", "flux", "sediment"), "balanced partition, 8 steps")
     assert ctx.far_fetch_count() >= 0
     ctx.close(); ref.close()
+
+
+def test_pack_device_is_the_texture_image(built, wet256):
+    """hg_pack_device -- the device-side half of hg_publish_gl (the other half is a copy into the mapped GL array,
+    which needs an OpenGL context) -- writes the field as an RGBA32F image into caller-provided DEVICE memory: it must
+    be byte for byte what hg_download returns, H.a included, for the grid fields and for the droplet mode's
+    texture-layout images."""
+    import torch
+    ctx = Context(256)
+    copy_state(wet256, ctx)
+    ctx.dispatch_grid()
+    for name in ("heightmap", "flux", "sediment"):
+        dev = torch.full((256, 256, 4), -1.0, dtype=torch.float32, device="cuda")
+        ctx.pack_device(FIELDS[name], dev.data_ptr())
+        ctx.sync()
+        assert_bit_equal(dev.cpu().numpy(), ctx.download(FIELDS[name]), f"pack_device {name}")
+    H = ctx.download(0)
+    assert np.array_equal(H[..., 3], (H[..., 0] + H[..., 1]) + H[..., 2])      # H.a as the last writer of a step leaves it
+    ctx.close()
+    p = Context(128, particle_count=1024, erosion_type=_lib.HG_PARTICLES)
+    m = p.get_map(); m.seed = SEED; m.hmap_dims[0], m.hmap_dims[1] = 128, 128; p.set_map(m)
+    p.gen_heightmap()
+    for k in range(3):
+        p.dispatch_particle((k + 1) * DT_TIME, True)
+    for name in ("heightmap", "velocity"):
+        dev = torch.zeros((128, 128, 4), dtype=torch.float32, device="cuda")
+        p.pack_device(FIELDS[name], dev.data_ptr())
+        p.sync()
+        assert_bit_equal(dev.cpu().numpy(), p.download(FIELDS[name]), f"pack_device {name} (droplet mode)")
+    p.close()
