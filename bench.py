@@ -400,8 +400,56 @@ def slab_parity(rig, W=1024, rows=512, steps=48):
     rig.barrier(slab)
     slab.close(); whole.close()
     all_ok = rig.reduce(1.0 if ok and errs == 0 else 0.0, "min") == 1.0
-    return {"result": "bit-identical" if all_ok else "MISMATCH", "what": f"{n} slabs of {W}x{rows} vs the whole {W}x{rows * n} map stepped on every rank's own GPU, "
-            f"{steps} main-loop steps (rain every 8), H/F/S compared bit for bit on every rank", "far_fetch_cells_all_ranks": rig.reduce(far, "sum")}
+    out = {"result": "bit-identical" if all_ok else "MISMATCH", "what": f"{n} slabs of {W}x{rows} vs the whole {W}x{rows * n} map stepped on every rank's own GPU, "
+           f"{steps} main-loop steps (rain every 8), H/F/S compared bit for bit on every rank", "far_fetch_cells_all_ranks": rig.reduce(far, "sum")}
+    out["droplets"] = droplet_slab_parity(rig)
+    return out
+
+
+def droplet_slab_parity(rig, W=512, rows=128, count=128, steps=60):
+    """The droplet mode on row slabs across processes (CUDA IPC): every rank steps its slab (hand-over of droplets,
+    peer atomics on the neighbours' edge texels, image exchanges) AND the whole map on its own GPU; in the sparse regime
+    (few droplets, result independent of their order) the droplets it owns, its rows of the heightmap and of the
+    momentum map must equal the whole-map run bit for bit."""
+    import numpy as np
+    from hydro_gen_b200 import Context, _lib, slabs
+    n = rig.world
+    H = rows * n
+
+    def setup(ctx):
+        m = ctx.get_map(); m.seed = SEED; m.hmap_dims[0], m.hmap_dims[1] = W, H; ctx.set_map(m)
+        ctx.gen_heightmap()
+
+    slab = Context(W, H, particle_count=count, erosion_type=_lib.HG_PARTICLES, device=rig.local, row0=rig.rank * rows, rows=rows)
+    slabs.connect_ring(slab, rig.dist, n, rig.rank)
+    setup(slab)
+    whole = Context(W, H, particle_count=count, erosion_type=_lib.HG_PARTICLES, device=rig.local)
+    setup(whole)
+    rig.barrier(slab)
+    own0 = slab.particle_owners()
+    moved = 0
+    for k in range(1, steps + 1):
+        slab.dispatch_particle(k * DT_TIME, True)
+        whole.dispatch_particle(k * DT_TIME, True)
+        if k % 10 == 0:
+            own = slab.particle_owners()
+            moved += int((own != own0).sum())
+            own0 = own
+    slab.sync()
+    own = slab.particle_owners().astype(bool)
+    a, b = slab.download_particles(), whole.download_particles()
+    ok = a[own].tobytes() == b[own].tobytes()
+    for f in (0, 2):
+        x, y = slab.download(f), whole.download(f)[rig.rank * rows:(rig.rank + 1) * rows]
+        ok = ok and bool(np.array_equal(x.view(np.uint32), y.view(np.uint32)))
+    errs = slab.slab_errors()
+    owned_total = rig.reduce(float(own.sum()), "sum")
+    rig.barrier(slab)
+    slab.close(); whole.close()
+    all_ok = rig.reduce(1.0 if ok and errs == 0 else 0.0, "min") == 1.0 and owned_total == count
+    return {"result": "bit-identical" if all_ok else "MISMATCH", "what": f"{count} droplets on {n} slabs of {W}x{rows}, {steps} Erosion::dispatch_particle steps, owned droplets and "
+            f"the slab's rows of H and M against the whole-map run on the same GPU", "droplets_with_exactly_one_owner": owned_total == count,
+            "ownership_changes_seen": rig.reduce(moved, "sum")}
 
 
 def main():

@@ -55,6 +55,12 @@ class SlabExport(C.Structure):
                 ("_pad", C.c_uint32)]
 
 
+class SlabExportParticles(C.Structure):
+    """hg_slab_export_particles_t: IPC handles of a droplet slab's texel images, droplet array and ownership bytes."""
+    _fields_ = [("images_handle", C.c_ubyte * 64), ("droplets_handle", C.c_ubyte * 64), ("owners_handle", C.c_ubyte * 64),
+                ("particle_count", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 assert C.sizeof(ErosionData) == 96 and C.sizeof(RainData) == 20 and C.sizeof(MapSettingsData) == 96
 
 # every symbol include/hydrogen_b200.h declares: (restype, argtypes)
@@ -109,6 +115,9 @@ SYMBOLS = {
     "hg_slab_set_ghost": (_i, [_vp, _i, _i, _vp]),
     "hg_slab_errors": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "hg_slab_refresh_halo": (_i, [_vp]),
+    "hg_slab_export_particles": (_i, [_vp, C.POINTER(SlabExportParticles)]),
+    "hg_slab_connect_particles": (_i, [_vp, C.POINTER(SlabExportParticles), _i, _i]),
+    "hg_slab_particle_owners": (_i, [_vp, _vp, _u]),
     "hg_register_gl": (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "hg_publish_gl": (_i, [_vp, _i]),
     "hg_unregister_gl": (_i, [_vp]),

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (ErosionData, MapSettingsData, RainData, SlabExport, check)
+from ._lib import (ErosionData, MapSettingsData, RainData, SlabExport, SlabExportParticles, check)
 
 PARTICLE_DTYPE = np.dtype([("sc", "<f4"), ("iters", "<i4"), ("position", "<f4", 2), ("velocity", "<f4", 2),
                            ("volume", "<f4"), ("_pad0", "<u4"), ("sediment", "<f4", 2), ("to_kill", "<u4"),
@@ -218,6 +218,19 @@ class Context:
     def connect(self, exports, my_index):
         arr = (SlabExport * len(exports))(*exports)
         check(self.L.hg_slab_connect(self.h, arr, len(exports), int(my_index)))
+
+    def export_particles(self):
+        e = SlabExportParticles(); check(self.L.hg_slab_export_particles(self.h, C.byref(e))); return e
+
+    def connect_particles(self, exports, my_index):
+        arr = (SlabExportParticles * len(exports))(*exports)
+        check(self.L.hg_slab_connect_particles(self.h, arr, len(exports), int(my_index)))
+
+    def particle_owners(self):
+        """1 per droplet this slab owns (holds the current state of); a whole map owns all"""
+        out = np.zeros(self.particle_count, dtype=np.uint8)
+        check(self.L.hg_slab_particle_owners(self.h, out.ctypes.data, self.particle_count))
+        return out
 
     def connect_local(self, contexts, my_index):
         arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])

@@ -34,6 +34,7 @@ static void free_ctx(hg_ctx* c) {
     if (c->aux) cudaFree(c->aux);
     if (c->particles) cudaFree(c->particles);
     if (c->pa) cudaFree(c->pa);
+    if (c->p_own) cudaFree(c->p_own);
     if (c->p_order) cudaFree(c->p_order);
     if (c->p_keys) cudaFree(c->p_keys);
     if (c->p_hist) cudaFree(c->p_hist);
@@ -102,6 +103,13 @@ static int create_impl(hg_ctx* c) {
     if (c->erosion_type == HG_PARTICLES) {
         int rc = hg_ensure_aux(c);   // momentum map + thermal planes
         if (rc) return rc;
+        if (c->g.row0 != 0 || c->g.rows != c->g.H) {
+            // a droplet SLAB: peers take the addresses of the texel images and of the ownership bytes at connect time
+            HG_CUDA(cudaMalloc(&c->pa, (size_t)4 * c->g.plane_elems * sizeof(float4)));
+            HG_CUDA(cudaMemsetAsync(c->pa, 0, (size_t)4 * c->g.plane_elems * sizeof(float4), c->stream));
+            HG_CUDA(cudaMalloc(&c->p_own, c->particle_count));
+            HG_CUDA(cudaMemsetAsync(c->p_own, 0, c->particle_count, c->stream));
+        }
     }
     HG_CUDA(cudaStreamSynchronize(c->stream));
     return HG_OK;
@@ -116,7 +124,6 @@ extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0,
     if (map_w > 1u << 20 || map_h > 1u << 20) { hg_set_error("map size %ux%u too large", map_w, map_h); return nullptr; }
     if (rows == 0 || (uint64_t)row0 + rows > map_h) { hg_set_error("slab rows [%u,%u) outside map height %u", row0, row0 + rows, map_h); return nullptr; }
     if (erosion_type != HG_GRID && erosion_type != HG_PARTICLES) { hg_set_error("unknown erosion type %d", erosion_type); return nullptr; }
-    if (erosion_type == HG_PARTICLES && (row0 != 0 || rows != map_h)) { hg_set_error("particle mode runs on a whole map only"); return nullptr; }
     if (erosion_type == HG_PARTICLES && particle_count == 0) { hg_set_error("particle mode needs particle_count > 0"); return nullptr; }
     hg_ctx* c = new (std::nothrow) hg_ctx();
     if (!c) { hg_set_error("out of host memory"); return nullptr; }
@@ -372,6 +379,16 @@ int transfer(hg_ctx* c, int field, float* host, bool upload) {
 
 }  // namespace
 
+int hg_preload_context_kernels(void) {
+    cudaFuncAttributes a;
+    HG_CUDA(cudaFuncGetAttributes(&a, k_pack));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_unpack));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_mass));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_planes_to_aos));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_aos_to_planes));
+    return HG_OK;
+}
+
 extern "C" int hg_upload_async(hg_ctx* c, int field, const float* src) { HG_CHECK_CTX(c); return transfer(c, field, const_cast<float*>(src), true); }
 extern "C" int hg_download_async(hg_ctx* c, int field, float* dst) { HG_CHECK_CTX(c); return transfer(c, field, dst, false); }
 extern "C" int hg_upload(hg_ctx* c, int field, const float* src) {
@@ -410,6 +427,10 @@ extern "C" int hg_upload_particles(hg_ctx* c, const hg_particle* src, uint32_t c
     if (!src || count > c->particle_count) { hg_set_error("bad particle upload (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
     HG_CUDA(cudaMemcpyAsync(c->particles, src, (size_t)count * sizeof(hg_particle), cudaMemcpyHostToDevice, c->stream));
     c->p_order_valid = false;      // positions changed under the processing order
+    if (c->p_own) {                // droplet slab: every slab receives the same array and takes the droplets in its rows
+        int rco = hg_particle_own_init(c);
+        if (rco) return rco;
+    }
     HG_CUDA(cudaStreamSynchronize(c->stream));
     return HG_OK;
 }
@@ -417,6 +438,15 @@ extern "C" int hg_download_particles(hg_ctx* c, hg_particle* dst, uint32_t count
     HG_CHECK_CTX(c);
     if (!dst || count > c->particle_count) { hg_set_error("bad particle download (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
     HG_CUDA(cudaMemcpyAsync(dst, c->particles, (size_t)count * sizeof(hg_particle), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    return HG_OK;
+}
+
+extern "C" int hg_slab_particle_owners(hg_ctx* c, unsigned char* dst, uint32_t count) {
+    HG_CHECK_CTX(c);
+    if (!dst || count > c->particle_count) { hg_set_error("bad owner download (count %u of %u)", count, c->particle_count); return HG_ERR_INVALID; }
+    if (!c->p_own) { memset(dst, 1, count); return HG_OK; }      // a whole map owns all its droplets
+    HG_CUDA(cudaMemcpyAsync(dst, c->p_own, count, cudaMemcpyDeviceToHost, c->stream));
     HG_CUDA(cudaStreamSynchronize(c->stream));
     return HG_OK;
 }
@@ -625,7 +655,38 @@ extern "C" int hg_dispatch_particle_pass(hg_ctx* c, int which, float time, int s
 extern "C" int hg_dispatch_particle(hg_ctx* c, float time, int should_rain) {
     HG_CHECK_CTX(c);
     if (c->erosion_type != HG_PARTICLES) { hg_set_error("dispatch_particle on a grid context"); return HG_ERR_STATE; }
-    int rc = hg_launch_particle_move(c, time, should_rain);
+    int rc;
+    if (c->g.row0 != 0 || c->g.rows != c->g.H) {
+        // droplets on row slabs: spawn + hand-over | all ranks | move, erode (+ hand-over of drifted droplets, NVLink
+        // atomics for corner texels in a neighbour's rows) | all ranks | edge rows of the eroded images | all ranks |
+        // thermal/smoothing tail | edge rows of the new images (the wait sits in front of the next dispatch)
+        if (!c->peers_connected) { hg_set_error("a droplet slab must be connected to its peers (hg_slab_connect*) before it steps"); return HG_ERR_STATE; }
+        if (c->schedule != HG_SCHEDULE_FUSED) { hg_set_error("droplet slabs run on the FUSED schedule"); return HG_ERR_STATE; }
+        rc = hg_slab_check_sticky(c);
+        if (rc) return rc;
+        rc = hg_particle_layout(c, true);
+        if (rc) return rc;
+        rc = hg_slab_wait_pending(c);
+        if (rc) return rc;
+        rc = hg_launch_particle_spawn(c, time, should_rain);
+        if (rc) return rc;
+        rc = hg_slab_barrier(c, false);
+        if (rc) return rc;
+        rc = hg_slab_wait_pending(c);
+        if (rc) return rc;
+        rc = hg_launch_particle_move(c, time, should_rain);
+        if (rc) return rc;
+        rc = hg_launch_particle_erode(c);
+        if (rc) return rc;
+        rc = hg_slab_barrier(c, false);
+        if (rc) return rc;
+        rc = hg_slab_push_images(c);      // waits for the generation above first
+        if (rc) return rc;
+        rc = hg_launch_fused_thermal_smooth_particle(c);      // waits for the pushed rows
+        if (rc) return rc;
+        return hg_slab_push_images(c);
+    }
+    rc = hg_launch_particle_move(c, time, should_rain);
     if (rc) return rc;
     rc = hg_launch_particle_erode(c);
     if (rc) return rc;

@@ -620,6 +620,21 @@ static int align_sets(hg_ctx* c) {
     return HG_OK;
 }
 
+// Under CUDA's lazy module loading the FIRST launch of a kernel loads its code, which can wait for kernels that are
+// running -- and a slab's stream may hold a spinning halo wait whose release needs another slab's launch from the same
+// host thread.  Connected contexts therefore load every kernel of the step path up front (hg_slab_connect*).
+int hg_preload_fused_kernels(void) {
+    cudaFuncAttributes a;
+    HG_CUDA(cudaFuncGetAttributes(&a, k_fused_ws<128, 3, 72, 88, false>));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_fused_ws<128, 3, 72, 88, true>));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_fused_ws2<128, 2, 120, 136>));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_far_fixup));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_plan_segments));
+    HG_CUDA(cudaFuncSetAttribute(k_fused_ws<128, 3, 72, 88, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem<128>::BYTES));
+    HG_CUDA(cudaFuncSetAttribute(k_fused_ws<128, 3, 72, 88, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem<128>::BYTES));
+    return HG_OK;
+}
+
 // drops = false: Erosion::dispatch_grid.  drops = true: the grid part of Erosion::dispatch_particle
 // (src/erosion.cpp:146-155: thermal x2 + smoothing with the momentum map) on the same kernel, the hydraulic warp
 // group only feeding (rock, dirt) to the thermal one; reads H and the momentum map, writes the other sets and H.a.
@@ -705,7 +720,9 @@ static int launch_fused(hg_ctx* c, bool drops) {
     // HG_FUSED_BALANCE=0 keep the uniform segments.
     bool balanced = false;
     PlanArgs plan_args{};
-    if ((v == 5 || two_lane) && c->tune_seg <= 0 && !c->no_balance) {
+    // (droplet slabs keep uniform segments: the first use of a plan allocates and synchronises, which a host thread
+    // driving several slabs of one process must not do between two exchange generations)
+    if ((v == 5 || two_lane) && c->tune_seg <= 0 && !c->no_balance && !(drops && c->peers_connected)) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // Only with at least six segments per strip: with fewer (16384 columns: 3.1 per strip) one segment more or

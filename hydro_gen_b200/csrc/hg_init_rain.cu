@@ -85,3 +85,10 @@ int hg_launch_rain(hg_ctx* c, float time) {
     if (!in_place) c->ri[0] ^= 1;
     return HG_OK;
 }
+
+int hg_preload_init_rain_kernels(void) {
+    cudaFuncAttributes a;
+    HG_CUDA(cudaFuncGetAttributes(&a, k_rain));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_heightmap));
+    return HG_OK;
+}

@@ -73,6 +73,13 @@ struct hg_ctx {
     bool p_aos;
     // droplet processing order (hg_particles.cu): droplet ids binned by map tile, so the threads of a warp gather from
     // and scatter to neighbouring texels; rebuilt every p_rebin_period dispatches (HG_DROPS_REBIN, 0 = id order)
+    // droplets on row slabs: ownership bytes (1 = this rank moves and erodes the droplet) and every rank's images,
+    // droplet array and ownership bytes (hg_slab_connect*)
+    unsigned char* p_own;
+    float4* peer_pa[HG_MAX_SLABS];
+    hg_particle* peer_parts[HG_MAX_SLABS];
+    unsigned char* peer_own[HG_MAX_SLABS];
+    bool peer_p_ipc[HG_MAX_SLABS];
     uint32_t* p_order;         // particle_count ids, or null
     uint32_t* p_keys;          // bin of every droplet (scratch)
     uint32_t* p_hist;          // bins + block sums (scratch)
@@ -182,9 +189,16 @@ int hg_launch_pass(hg_ctx* c, int pass);
 int hg_launch_fused_step(hg_ctx* c);
 int hg_launch_rain(hg_ctx* c, float time);
 int hg_launch_heightmap(hg_ctx* c);
+int hg_launch_particle_spawn(hg_ctx* c, float time, int should_rain);   // slabs: respawn + hand-over before the move
+int hg_particle_own_init(hg_ctx* c);
+int hg_slab_push_images(hg_ctx* c);   // droplet slabs: edge rows of the H and M images to the neighbours' ghost rows + signal
 int hg_launch_particle_move(hg_ctx* c, float time, int should_rain);
 int hg_launch_particle_erode(hg_ctx* c);
 int hg_launch_thermal_smooth_particle(hg_ctx* c);
+int hg_preload_fused_kernels(void);      // force-load kernels (lazy module loading must not happen under a spinning halo wait)
+int hg_preload_particle_kernels(void);
+int hg_preload_init_rain_kernels(void);
+int hg_preload_context_kernels(void);
 int hg_slab_exchange(hg_ctx* c);     // push edge rows to neighbours + wait (no-op without peers)
 int hg_slab_barrier(hg_ctx* c, bool push);   // generation signal + all-rank wait, with or without the edge-row push
 int hg_slab_wait_pending(hg_ctx* c); // enqueue the wait for the last signalled generation (before rain / a step touches the planes)

@@ -25,8 +25,43 @@
 
 namespace {
 
-struct PDom { int W, H, pitch; };
-__device__ __forceinline__ size_t pidx(const PDom& d, int x, int y) { return (size_t)(y + HG_HALO_ROWS) * d.pitch + x; }
+struct PDom { int W, H, pitch, row0; };      // global map size; first owned row of this context's images (ghost rows below it)
+__device__ __forceinline__ size_t pidx(const PDom& d, int x, int y) { return (size_t)(y - d.row0 + HG_HALO_ROWS) * d.pitch + x; }
+
+// Droplets on row slabs: every rank keeps the whole droplet array (the id is part of a
+// droplet's identity: spawn hash) but owns -- moves and erodes -- only the droplets whose position lies in its rows;
+// own[id] says which.  A droplet that respawns or drifts into another slab is handed over by writing its element and
+// the two ownership bytes through the peer pointers; a corner texel in a neighbour's rows is eroded in the
+// neighbour's image directly (atomics work over NVLink), so the texel stays ONE location with the lock's semantics.
+struct PSlabs {
+    int n, me;
+    int row0[HG_MAX_SLABS], rows[HG_MAX_SLABS];
+    float4* ha[HG_MAX_SLABS];            // read images of every slab (same set index on all ranks)
+    float4* ma[HG_MAX_SLABS];
+    hg_particle* parts[HG_MAX_SLABS];
+    unsigned char* own[HG_MAX_SLABS];
+};
+__device__ __forceinline__ int slab_of_row(const PSlabs& S, int y) {
+    int k = S.me;
+    if (y < S.row0[k] || y >= S.row0[k] + S.rows[k]) {
+        k = y < S.row0[0] ? 0 : S.n - 1;
+        for (int j = 0; j < S.n; j++)
+            if (y >= S.row0[j] && y < S.row0[j] + S.rows[j]) { k = j; break; }
+    }
+    return k;
+}
+// hand droplet `id` (state p) to the slab that holds its position; returns true if it left this slab
+__device__ __forceinline__ void slab_store_droplet(const PSlabs& S, uint32_t id, const hg_particle& p, int H) {
+    int y = (int)p.position[1];
+    y = min(max(y, 0), H - 1);
+    const int o = slab_of_row(S, y);
+    S.parts[o][id] = p;
+    if (o != S.me) {
+        __threadfence_system();          // the element before the ownership byte
+        S.own[o][id] = 1;
+        S.own[S.me][id] = 0;
+    }
+}
 __device__ __forceinline__ bool poob(const PDom& d, int x, int y) { return x < 0 || x > d.W - 1 || y < 0 || y > d.H - 1; }
 // texelFetch outside the image is 0 (hazard 3)
 __device__ __forceinline__ float2 fetch_xy(const float4* __restrict__ img, const PDom& d, int x, int y) {
@@ -57,7 +92,27 @@ __device__ __forceinline__ float prand(float px, float py) {
     return hg_fract(1e4f * hg_sinf(17.0f * px + py * 0.1f) * (0.1f + fabsf(hg_sinf(py * 13.0f + px))));
 }
 
-struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t* order; };
+struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t* order; const unsigned char* own; };
+
+// The spawn half of particle.glsl:64-90 on its own, for slabs: a droplet that (re)spawns gets its hashed position
+// anywhere on the map and must be with its new owner BEFORE it moves (the move samples the terrain around it).
+__global__ void __launch_bounds__(128) k_particle_spawn(PSlabs S, int H, hg_erosion_data set, hg_map_settings_data map_set, uint32_t count, float time, int should_rain) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count || !S.own[S.me][id] || !should_rain) return;       // without rain the shader returns before it stores anything
+    hg_particle p = S.parts[S.me][id];
+    if (!(p.iters == 0 || p.to_kill)) return;
+#pragma unroll
+    for (int i = 0; i < HG_SED_LAYERS; i++)
+        if (p.sediment[i] < 0.0f || p.iters == 0) p.sediment[i] = 0.0f;
+    float posx = prand(hg_fract(time * 1.37f) * 1000.0f, (float)id) * (float)((float)map_set.hmap_dims[0] - 4.0f) / 1.0f + 2.0f;
+    float posy = prand(hg_fract(time * 7.21f) * 1000.0f, (float)id + 3.14f) * (float)((float)map_set.hmap_dims[1] - 4.0f) / 1.0f + 2.0f;
+    p.to_kill = 0;
+    p.position[0] = posx; p.position[1] = posy;
+    p.velocity[0] = 0.0f; p.velocity[1] = 0.0f;
+    p.volume = set.init_volume;
+    p.iters = 1;
+    slab_store_droplet(S, id, p, H);
+}
 
 // particle.glsl:64-136
 __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, hg_erosion_data set, hg_map_settings_data map_set,
@@ -65,6 +120,7 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
     if (A.order) id = A.order[id];      // thread k takes the k-th droplet in tile order; the droplet keeps its id (spawn hash)
+    if (A.own && !A.own[id]) return;    // slabs: another rank's droplet
     hg_particle p = A.particles[id];
     if (p.iters == 0 && !should_rain) return;
 #pragma unroll
@@ -142,21 +198,21 @@ struct CornerAdd { float rock, dirt, water, mz, mw; };
 
 // (rock, dirt, water, -) += on the heightmap texel and (acc_x, acc_y) += on the momentum texel: two vector reductions.
 // A layer without a deposit adds +0.0f, which leaves every value as it is.
-__device__ __forceinline__ void texel_add(const ErodeImages& A, size_t ti, float rock, float dirt, float water, float mz, float mw) {
-    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(A.ha + ti), "f"(rock), "f"(dirt), "f"(water), "f"(0.0f) : "memory");
-    asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(reinterpret_cast<float*>(A.ma + ti) + 2), "f"(mz), "f"(mw) : "memory");
+__device__ __forceinline__ void texel_add(float4* hp, float4* mp, float rock, float dirt, float water, float mz, float mw) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(hp), "f"(rock), "f"(dirt), "f"(water), "f"(0.0f) : "memory");
+    asm volatile("red.global.v2.f32.add [%0], {%1, %2};" ::"l"(reinterpret_cast<float*>(mp) + 2), "f"(mz), "f"(mw) : "memory");
 }
 
 // Apply the corner additions of all 32 lanes.  Lanes of the warp that hit the same texel are found with ONE
 // match per corner; the lowest such lane sums its peers' five values in lane order and issues the two reductions.
 // All 32 lanes must call.
-__device__ __forceinline__ void warp_corner_add(const ErodeImages& A, size_t ti, const CornerAdd& v, bool act) {
+__device__ __forceinline__ void warp_corner_add(float4* hp, float4* mp, const CornerAdd& v, bool act) {
     const int lane = threadIdx.x & 31;
-    unsigned long long key = act ? (unsigned long long)ti : ~0ull - lane;
+    unsigned long long key = act ? (unsigned long long)hp : (unsigned long long)lane;      // a texel address is never < 32
     unsigned peers = __match_any_sync(0xffffffffu, key);
     if (!act) return;
     if (__popc(peers) == 1) {              // the common case on a sparse map: nobody else in the warp hits this texel
-        texel_add(A, ti, v.rock, v.dirt, v.water, v.mz, v.mw);
+        texel_add(hp, mp, v.rock, v.dirt, v.water, v.mz, v.mw);
         return;
     }
     // peers > 1 only occurs among active lanes (inactive keys are unique)
@@ -171,7 +227,7 @@ __device__ __forceinline__ void warp_corner_add(const ErodeImages& A, size_t ti,
         s_mz += __shfl_sync(peers, v.mz, src);
         s_mw += __shfl_sync(peers, v.mw, src);
     }
-    if (lane == __ffs(peers) - 1) texel_add(A, ti, s_rock, s_dirt, s_water, s_mz, s_mw);
+    if (lane == __ffs(peers) - 1) texel_add(hp, mp, s_rock, s_dirt, s_water, s_mz, s_mw);
 }
 
 // terr -= eroded with the exhausted-layer clamp of particle_erosion.glsl:53-59, as one
@@ -232,11 +288,22 @@ __device__ __forceinline__ void warp_erode(float* addr, float eroded, bool on, f
 
 struct ErodeArgs : ErodeImages { hg_particle* particles; const uint32_t* order; };
 
+// the heightmap / momentum texel (x, y) wherever it lives: this slab's images, or the owning rank's through its peer pointer
+template <bool SLAB>
+__device__ __forceinline__ void texel_ptrs(const ErodeArgs& A, const PSlabs& S, const PDom& d, int x, int y, float4** hp, float4** mp) {
+    if (!SLAB) { const size_t ti = pidx(d, x, y); *hp = A.ha + ti; *mp = A.ma + ti; return; }
+    const int k = slab_of_row(S, y);
+    const size_t ti = (size_t)(y - S.row0[k] + HG_HALO_ROWS) * d.pitch + x;
+    *hp = S.ha[k] + ti; *mp = S.ma[k] + ti;
+}
+
 // particle_erosion.glsl:101-128 + erode_layers :22-85
-__global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, ErodeArgs A, uint32_t count) {
+template <bool SLAB>
+__global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, ErodeArgs A, uint32_t count, const __grid_constant__ PSlabs S) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = id < count;
     if (live && A.order) id = A.order[id];
+    if (SLAB) live = live && S.own[S.me][id];
     hg_particle part = {};
     if (live) part = A.particles[id];
     live = live && part.iters != 0;
@@ -257,7 +324,8 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
         float wx = (k == 1 || k == 2) ? offx : 1.0f - offx;
         float wy = (k >= 2) ? offy : 1.0f - offy;
         bool act = live && !(cx < 0 || cx > d.W - 1 || cy < 0 || cy > d.H - 1);
-        size_t ti = act ? pidx(d, cx, cy) : 0;
+        float4 *hp = nullptr, *mp = nullptr;
+        if (act) texel_ptrs<SLAB>(A, S, d, cx, cy, &hp, &mp);
         float multipl = wx * wy;
         float dep[2] = {0.0f, 0.0f};      // value-independent additions to terrain, per layer
         // erode_layers (particle_erosion.glsl:22-85) layer by layer with every lane of the warp in step, because the
@@ -277,7 +345,7 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
             const bool erode = open && !kill && c > s1;
             const float eroded = erode ? multipl * P.Kls[i] * (c - s1) : 0.0f;
             float old_terr = 0.0f, after = 0.0f;
-            warp_erode(reinterpret_cast<float*>(A.ha + ti) + i, eroded, erode, &old_terr, &after);      // .x rock, .y dirt
+            warp_erode(reinterpret_cast<float*>(hp) + i, eroded, erode, &old_terr, &after);      // .x rock, .y dirt
             if (erode) {
                 s1 += eroded;
                 if (after < 0.0f) {
@@ -305,9 +373,12 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
         v.water = 1e-5f * part.volume * multipl;
         v.mz = part.volume * part.velocity[0] * multipl;
         v.mw = part.volume * part.velocity[1] * multipl;
-        warp_corner_add(A, ti, v, act);
+        warp_corner_add(hp, mp, v, act);
     }
-    if (live) A.particles[id] = part;
+    if (live) {
+        if (SLAB) slab_store_droplet(S, id, part, d.H);      // stays, or goes to the slab it drifted into
+        else A.particles[id] = part;
+    }
 }
 
 
@@ -417,38 +488,107 @@ static int rebuild_order(hg_ctx* c, uint32_t count) {
     return HG_OK;
 }
 
+// the droplet view of the slab table: every rank's read images, droplet array and ownership bytes
+static PSlabs make_pslabs(hg_ctx* c) {
+    PSlabs S;
+    memset(&S, 0, sizeof(S));
+    S.n = c->slabs.n; S.me = c->slabs.me;
+    for (int k = 0; k < S.n; k++) {
+        S.row0[k] = c->slabs.row0[k]; S.rows[k] = c->slabs.rows[k];
+        const size_t pe = (size_t)(c->slabs.rows[k] + 2 * HG_HALO_ROWS) * c->g.pitch;      // texels per image of slab k
+        S.ha[k] = c->peer_pa[k] + (size_t)c->ri[0] * pe;              // every rank flips its read indices in step
+        S.ma[k] = c->peer_pa[k] + (size_t)(2 + c->ri[2]) * pe;
+        S.parts[k] = c->peer_parts[k];
+        S.own[k] = c->peer_own[k];
+    }
+    return S;
+}
+static bool droplet_slabs(const hg_ctx* c) { return c->erosion_type == HG_PARTICLES && c->peers_connected; }
+
+// slabs only: respawn + hand-over of the droplets this rank owns (the first half of particle.glsl's main)
+int hg_launch_particle_spawn(hg_ctx* c, float time, int should_rain) {
+    uint32_t count = (c->particle_count / 64u) * 64u;
+    if (!count || !droplet_slabs(c)) return HG_OK;
+    k_particle_spawn<<<(count + 127) / 128, 128, 0, c->stream>>>(make_pslabs(c), c->g.H, c->erosion, c->map, count, time, should_rain);
+    HG_LAUNCH_CHECK(c);
+    return HG_OK;
+}
+
 int hg_launch_particle_move(hg_ctx* c, float time, int should_rain) {
-    PDom d{c->g.W, c->g.H, c->g.pitch};
+    PDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0};
     uint32_t count = (c->particle_count / 64u) * 64u;    // glDispatchCompute(particle_count/64), erosion.cpp:127
     if (!count) return HG_OK;
     int rc = hg_particle_layout(c, true);
     if (rc) return rc;
+    const bool slabs = droplet_slabs(c);
     // processing order: rebuilt when it has aged; a fresh context (nothing spawned yet) moves in id order and sorts
-    // after the move, when the droplets have their spawn positions (hg_launch_particle_erode)
-    if (c->p_rebin_period > 0 && c->p_order_valid && ++c->p_rebin_age >= c->p_rebin_period) {
+    // after the move, when the droplets have their spawn positions (hg_launch_particle_erode).  Slabs process their
+    // droplets in id order (ownership changes every step).
+    if (!slabs && c->p_rebin_period > 0 && c->p_order_valid && ++c->p_rebin_age >= c->p_rebin_period) {
         rc = rebuild_order(c, count);
         if (rc) return rc;
     }
-    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, c->p_order_valid ? c->p_order : nullptr};
+    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, (!slabs && c->p_order_valid) ? c->p_order : nullptr, slabs ? c->p_own : nullptr};
     k_particle_move<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, c->erosion, c->map, A, count, time, should_rain);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
 }
 
 int hg_launch_particle_erode(hg_ctx* c) {
-    PDom d{c->g.W, c->g.H, c->g.pitch};
+    PDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0};
     uint32_t count = (c->particle_count / 64u) * 64u;
     if (!count) return HG_OK;
     // in place on the READ images of heightmap and momentum map (erosion.cpp:141-143)
     int rc = hg_particle_layout(c, true);
     if (rc) return rc;
-    if (c->p_rebin_period > 0 && !c->p_order_valid) {
+    const bool slabs = droplet_slabs(c);
+    if (!slabs && c->p_rebin_period > 0 && !c->p_order_valid) {
         rc = rebuild_order(c, count);
         if (rc) return rc;
     }
     ErodeArgs A;
-    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = c->p_order_valid ? c->p_order : nullptr;
-    k_particle_erode<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count);
+    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = (!slabs && c->p_order_valid) ? c->p_order : nullptr;
+    if (slabs) {
+        k_particle_erode<true><<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count, make_pslabs(c));
+    } else {
+        PSlabs none;
+        memset(&none, 0, sizeof(none));
+        k_particle_erode<false><<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count, none);
+    }
     HG_LAUNCH_CHECK(c);
+    return HG_OK;
+}
+
+// ownership at connect time: unspawned droplets are dealt out round robin (their first position is a hash of the id)
+__global__ void k_own_init(unsigned char* own, uint32_t count, int n, int me) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id < count) own[id] = (int)(id % (uint32_t)n) == me ? 1 : 0;
+}
+// ownership after the droplet array was replaced from outside (hg_upload_particles on every slab, checkpoint load):
+// a spawned droplet belongs to the slab that holds its row, an unspawned one is dealt out as at connect time
+__global__ void k_own_from_positions(PSlabs S, int H, uint32_t count) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= count) return;
+    const hg_particle p = S.parts[S.me][id];
+    int o = (int)(id % (uint32_t)S.n);
+    if (p.iters != 0) o = slab_of_row(S, min(max((int)p.position[1], 0), H - 1));
+    S.own[S.me][id] = o == S.me ? 1 : 0;
+}
+int hg_particle_own_init(hg_ctx* c) {
+    if (!c->p_own || !c->particle_count) return HG_OK;
+    if (c->peers_connected && c->peer_parts[c->slabs.me]) k_own_from_positions<<<(c->particle_count + 255) / 256, 256, 0, c->stream>>>(make_pslabs(c), c->g.H, c->particle_count);
+    else k_own_init<<<(c->particle_count + 255) / 256, 256, 0, c->stream>>>(c->p_own, c->particle_count, c->slabs.n > 0 ? c->slabs.n : 1, c->slabs.me);
+    HG_LAUNCH_CHECK(c);
+    return HG_OK;
+}
+
+int hg_preload_particle_kernels(void) {
+    cudaFuncAttributes a;
+    HG_CUDA(cudaFuncGetAttributes(&a, k_particle_spawn));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_particle_move));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_particle_erode<true>));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_particle_erode<false>));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_own_init));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_own_from_positions));
     return HG_OK;
 }

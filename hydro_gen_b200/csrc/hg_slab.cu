@@ -99,8 +99,22 @@ inline size_t plane_elems_of(const hg_ctx* c, int k) { return (size_t)(c->slabs.
 
 }  // namespace
 
+static int preload_step_kernels(hg_ctx* c) {
+    cudaFuncAttributes a;
+    HG_CUDA(cudaFuncGetAttributes(&a, k_halo_push_signal));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_halo_wait));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_halo_signal));
+    int rc = hg_preload_fused_kernels();
+    if (rc == HG_OK) rc = hg_preload_init_rain_kernels();
+    if (rc == HG_OK) rc = hg_preload_context_kernels();
+    if (rc == HG_OK && c->erosion_type == HG_PARTICLES) rc = hg_preload_particle_kernels();
+    return rc;
+}
+
 // The sticky error word of k_halo_wait: mapped pinned host memory, so the host reads it without synchronising.
 static int ensure_sticky(hg_ctx* c) {
+    int rcp = preload_step_kernels(c);      // every connect: cheap once the kernels are loaded
+    if (rcp) return rcp;
     if (c->h_sticky) return HG_OK;
     HG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_sticky), sizeof(unsigned), cudaHostAllocMapped));
     *c->h_sticky = 0u;
@@ -188,15 +202,65 @@ extern "C" int hg_slab_connect_local(hg_ctx* c, hg_ctx* const* all, int n, int m
         c->slabs.arena[k] = all[k]->arena;
         c->slabs.row0[k] = row0[k]; c->slabs.rows[k] = rows[k];
         c->slab_ipc[k] = false;
+        if (c->erosion_type == HG_PARTICLES) {
+            if (all[k]->erosion_type != HG_PARTICLES || all[k]->particle_count != c->particle_count || !all[k]->pa || !all[k]->p_own) {
+                hg_set_error("slab %d is not a droplet slab with %u droplets", k, c->particle_count);
+                return HG_ERR_INVALID;
+            }
+            c->peer_pa[k] = all[k]->pa; c->peer_parts[k] = all[k]->particles; c->peer_own[k] = all[k]->p_own;
+            c->peer_p_ipc[k] = false;
+        }
     }
     c->slabs.n = n; c->slabs.me = me;
     c->peers_connected = n > 1;
+    if (c->erosion_type == HG_PARTICLES) {
+        int rco = hg_particle_own_init(c);
+        if (rco) return rco;
+    }
     return ensure_sticky(c);
+}
+
+// The droplet mode's three extra allocations (texel images, droplet array, ownership bytes) between processes.
+extern "C" int hg_slab_export_particles(hg_ctx* c, hg_slab_export_particles_t* out) {
+    HG_CHECK_CTX(c);
+    if (!out) return HG_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    if (c->erosion_type != HG_PARTICLES || !c->pa || !c->p_own) { hg_set_error("not a droplet slab"); return HG_ERR_STATE; }
+    cudaIpcMemHandle_t h;
+    HG_CUDA(cudaIpcGetMemHandle(&h, c->pa)); memcpy(out->images_handle, &h, sizeof(h));
+    HG_CUDA(cudaIpcGetMemHandle(&h, c->particles)); memcpy(out->droplets_handle, &h, sizeof(h));
+    HG_CUDA(cudaIpcGetMemHandle(&h, c->p_own)); memcpy(out->owners_handle, &h, sizeof(h));
+    out->particle_count = c->particle_count;
+    return HG_OK;
+}
+// after hg_slab_connect: all[0..n) in the same order
+extern "C" int hg_slab_connect_particles(hg_ctx* c, const hg_slab_export_particles_t* all, int n, int me) {
+    HG_CHECK_CTX(c);
+    if (!all || n != c->slabs.n || me != c->slabs.me || c->erosion_type != HG_PARTICLES) { hg_set_error("hg_slab_connect_particles: call hg_slab_connect first, with the same table order"); return HG_ERR_STATE; }
+    for (int k = 0; k < n; k++) {
+        if (all[k].particle_count != c->particle_count) { hg_set_error("slab %d holds %u droplets, this one %u", k, all[k].particle_count, c->particle_count); return HG_ERR_INVALID; }
+        if (k == me) { c->peer_pa[k] = c->pa; c->peer_parts[k] = c->particles; c->peer_own[k] = c->p_own; c->peer_p_ipc[k] = false; continue; }
+        cudaIpcMemHandle_t h;
+        void* p = nullptr;
+        memcpy(&h, all[k].images_handle, sizeof(h)); HG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); c->peer_pa[k] = static_cast<float4*>(p);
+        memcpy(&h, all[k].droplets_handle, sizeof(h)); HG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); c->peer_parts[k] = static_cast<hg_particle*>(p);
+        memcpy(&h, all[k].owners_handle, sizeof(h)); HG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); c->peer_own[k] = static_cast<unsigned char*>(p);
+        c->peer_p_ipc[k] = true;
+    }
+    return hg_particle_own_init(c);
 }
 
 void hg_slab_disconnect(hg_ctx* c) {
     for (int k = 0; k < c->slabs.n; k++)
         if (c->slab_ipc[k] && c->slabs.arena[k]) cudaIpcCloseMemHandle(c->slabs.arena[k]);
+    for (int k = 0; k < HG_MAX_SLABS; k++)
+        if (c->peer_p_ipc[k]) {
+            if (c->peer_pa[k]) cudaIpcCloseMemHandle(c->peer_pa[k]);
+            if (c->peer_parts[k]) cudaIpcCloseMemHandle(c->peer_parts[k]);
+            if (c->peer_own[k]) cudaIpcCloseMemHandle(c->peer_own[k]);
+        }
+    memset(c->peer_pa, 0, sizeof(c->peer_pa)); memset(c->peer_parts, 0, sizeof(c->peer_parts));
+    memset(c->peer_own, 0, sizeof(c->peer_own)); memset(c->peer_p_ipc, 0, sizeof(c->peer_p_ipc));
     memset(&c->slabs, 0, sizeof(c->slabs));
     memset(c->slab_ipc, 0, sizeof(c->slab_ipc));
     c->peers_connected = false;
@@ -222,12 +286,17 @@ int hg_slab_check_sticky(hg_ctx* c) {
 }
 
 int hg_slab_exchange(hg_ctx* c) { return hg_slab_barrier(c, true); }
+static int slab_generation(hg_ctx* c, int mode);
+int hg_slab_barrier(hg_ctx* c, bool push) { return slab_generation(c, push ? 1 : 0); }
+int hg_slab_push_images(hg_ctx* c) { return slab_generation(c, 2); }
 
 // After a fused step (push = true): push my new edge rows to both neighbours and publish the generation on
 // every rank; the wait until every rank has published it is enqueued in front of the next step (hg_slab_wait_pending).  push = false: only the
 // generation signal + wait, an all-rank barrier on the device (after an in-place rain: a peer's far fetch of
 // the next step must not read this rank's water before the rain has been added).
-int hg_slab_barrier(hg_ctx* c, bool push) {
+// mode 0: signal only; 1: push the nine planes; 2: push the droplet mode's heightmap and momentum images
+static int slab_generation(hg_ctx* c, int mode) {
+    const bool push = mode != 0;
     if (!c->peers_connected) return HG_OK;
     int rcw = hg_slab_wait_pending(c);      // generations are waited for in order
     if (rcw) return rcw;
@@ -237,19 +306,31 @@ int hg_slab_barrier(hg_ctx* c, bool push) {
     const size_t rowsz = (size_t)c->g.pitch;
     PushArgs A;
     memset(&A, 0, sizeof(A));
-    for (int p = 0; p < HG_NPLANES; p++) A.src[p] = hg_plane(c, c->ri[hg_field_of_plane(p)], p);
-    A.n = (size_t)HG_HALO_ROWS * rowsz;
-    for (int s = 0; s < 2; s++) {
+    // elements per row of a "plane": 1 float per cell, or 4 for a texel image (droplet mode: H image, M image)
+    const size_t per = mode == 2 ? 4 : 1;
+    if (mode == 2) {
+        A.src[0] = reinterpret_cast<const float*>(hg_pa_h(c, 1));
+        A.src[1] = reinterpret_cast<const float*>(hg_pa_m(c, 1));
+    } else {
+        for (int p = 0; p < HG_NPLANES; p++) A.src[p] = hg_plane(c, c->ri[hg_field_of_plane(p)], p);
+    }
+    A.n = (size_t)HG_HALO_ROWS * rowsz * per;
+    for (int s = 0; push && s < 2; s++) {
         int nb = T.me + (s == 0 ? -1 : 1);
         if (nb < 0 || nb >= T.n) continue;
         size_t nb_elems = plane_elems_of(c, nb);
-        for (int p = 0; p < HG_NPLANES; p++)
-            A.side[s].dst[p] = T.arena[nb] + ((size_t)c->ri[hg_field_of_plane(p)] * HG_NPLANES + p) * nb_elems;
+        if (mode == 2) {
+            A.side[s].dst[0] = reinterpret_cast<float*>(c->peer_pa[nb] + (size_t)c->ri[0] * nb_elems);
+            A.side[s].dst[1] = reinterpret_cast<float*>(c->peer_pa[nb] + (size_t)(2 + c->ri[2]) * nb_elems);
+        } else {
+            for (int p = 0; p < HG_NPLANES; p++)
+                A.side[s].dst[p] = T.arena[nb] + ((size_t)c->ri[hg_field_of_plane(p)] * HG_NPLANES + p) * nb_elems;
+        }
         if (s == 0) {   // my first owned rows -> lower neighbour's upper ghost rows
-            A.side[s].src_off = (size_t)HG_HALO_ROWS * rowsz;
-            A.side[s].dst_off = (size_t)(HG_HALO_ROWS + T.rows[nb]) * rowsz;
+            A.side[s].src_off = (size_t)HG_HALO_ROWS * rowsz * per;
+            A.side[s].dst_off = (size_t)(HG_HALO_ROWS + T.rows[nb]) * rowsz * per;
         } else {        // my last owned rows -> upper neighbour's lower ghost rows
-            A.side[s].src_off = (size_t)c->g.rows * rowsz;
+            A.side[s].src_off = (size_t)c->g.rows * rowsz * per;
             A.side[s].dst_off = 0;
         }
     }

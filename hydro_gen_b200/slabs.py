@@ -48,4 +48,33 @@ def connect_ring(ctx, dist, world, rank):
     check_exports(exports, ctx.W, ctx.H)
     if world > 1:
         ctx.connect(exports, rank)
+        if ctx.particle_count and ctx.erosion_type == _lib.HG_PARTICLES:
+            # droplet slabs: the texel images, the droplet array and the ownership bytes travel the same way
+            pblobs = gather_exports(bytes(ctx.export_particles()), dist, world)
+            ctx.connect_particles([_lib.SlabExportParticles.from_buffer_copy(b) for b in pblobs], rank)
     return exports
+
+
+def owner_of_row(row, table):
+    """index of the slab (row0, rows) that holds map row `row`: the rank that owns a droplet at that row"""
+    for k, (row0, rows) in enumerate(table):
+        if row0 <= row < row0 + rows:
+            return k
+    raise ValueError(f"row {row} is outside every slab")
+
+
+def merge_droplets(parts_per_slab, owners_per_slab):
+    """The droplet array of the whole map from the slabs' arrays: element id comes from the slab that owns it.
+    Raises if a droplet has no owner or several (the hand-over invariant)."""
+    import numpy as np
+    own = np.stack(owners_per_slab).astype(np.int32)
+    n_owner = own.sum(axis=0)
+    if not np.all(n_owner == 1):
+        bad = np.flatnonzero(n_owner != 1)
+        raise ValueError(f"{bad.size} droplets do not have exactly one owner (first: id {bad[0]} has {n_owner[bad[0]]})")
+    who = own.argmax(axis=0)
+    out = parts_per_slab[0].copy()
+    for k, p in enumerate(parts_per_slab):
+        sel = who == k
+        out[sel] = p[sel]
+    return out

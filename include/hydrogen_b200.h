@@ -186,6 +186,22 @@ int hg_slab_export_handle(hg_ctx* ctx, hg_slab_export* out);
  * arena is mapped so a sediment back-trace that leaves the slab can be resolved by a
  * direct peer load (far fetch). */
 int hg_slab_connect(hg_ctx* ctx, const hg_slab_export* all, int n, int my_index);
+/* Droplet mode on slabs: every rank keeps the whole droplet array and owns the droplets whose position
+ * lies in its rows; droplets that respawn or drift across a slab edge are handed over through peer pointers, corner
+ * texels in a neighbour's rows are eroded in the neighbour's image (NVLink atomics), and the heightmap / momentum
+ * images exchange their edge rows after the erode pass and after the thermal/smoothing tail.  Between processes the
+ * three extra allocations travel like the arena: export, all-gather, connect (after hg_slab_connect). */
+typedef struct hg_slab_export_particles_t {
+    unsigned char images_handle[HG_IPC_HANDLE_BYTES];
+    unsigned char droplets_handle[HG_IPC_HANDLE_BYTES];
+    unsigned char owners_handle[HG_IPC_HANDLE_BYTES];
+    uint32_t particle_count;
+    uint32_t _pad;
+} hg_slab_export_particles_t;
+int hg_slab_export_particles(hg_ctx* ctx, hg_slab_export_particles_t* out);
+int hg_slab_connect_particles(hg_ctx* ctx, const hg_slab_export_particles_t* all, int n, int my_index);
+/* 1 byte per droplet: 1 = this slab owns (moves and erodes) the droplet and holds its current state.  Blocking. */
+int hg_slab_particle_owners(hg_ctx* ctx, unsigned char* dst, uint32_t count);
 /* Same, for slabs that live in THIS process (one host thread driving several GPUs, or
  * several slabs on one GPU in the tests): CUDA IPC handles cannot be opened by the
  * process that created them. */

@@ -153,3 +153,70 @@ def test_particle_tail_fused_equals_passes(built):
     H0 = ref.get(0)
     assert np.abs(a.download(FIELDS["velocity"])).max() > 0
     a.close(); b.close(); ref.close()
+
+
+def test_droplet_slabs_match_whole_map(built):
+    """Droplet mode on row slabs: three slabs in one process (peer pointers) against the
+    whole-map run, in the sparse regime where the result is order-free: droplet array (merged from the owners), the
+    heightmap and the momentum map must be identical bit for bit after every dispatch.  The droplets are placed along
+    the two slab edges and given velocities across them, so the run exercises what sharding adds: hand-over of drifting
+    and respawning droplets, erosion of corner texels in the neighbour's rows (NVLink-style peer atomics), the gather
+    halo of the move pass and the two image exchanges per step."""
+    from hydro_gen_b200 import slabs as slabmod
+    n, count = 256, 64
+    cuts = [0, 88, 176, 256]
+    table = [(cuts[i], cuts[i + 1] - cuts[i]) for i in range(3)]
+
+    def setup(c):
+        m = c.get_map(); m.seed = SEED; m.hmap_dims[0], m.hmap_dims[1] = n, n; c.set_map(m)
+        e = c.get_erosion(); e.Kalpha[0], e.Kalpha[1] = 0.5, 0.2; c.set_erosion(e)      # both thermal layers move terrain
+        c.gen_heightmap()
+
+    whole = Context(n, particle_count=count, erosion_type=_lib.HG_PARTICLES)
+    setup(whole)
+    parts = [Context(n, n, particle_count=count, erosion_type=_lib.HG_PARTICLES, row0=r0, rows=rows) for r0, rows in table]
+    for i, s in enumerate(parts):
+        s.connect_local(parts, i)
+    for s in parts:
+        setup(s)
+    crossings = 0
+    owners_before = None
+    for k in range(1, 41):
+        t = float(np.float32(k) * np.float32(DT_TIME))
+        if k == 3:
+            # move the droplets onto the slab edges with velocities across them (same state everywhere; the owner of
+            # each is the slab that holds its row, which is what the hand-over rule keeps true)
+            P = whole.download_particles()
+            rng = np.random.default_rng(11)
+            edge = np.where(np.arange(count) % 2 == 0, cuts[1], cuts[2]).astype(np.float32)
+            P["position"][:, 1] = edge + rng.uniform(-0.6, 0.6, count).astype(np.float32)
+            P["position"][:, 0] = np.linspace(8, n - 8, count).astype(np.float32)      # far apart in x: sparse
+            P["velocity"][:, 1] = np.where(rng.random(count) < 0.5, 0.9, -0.9).astype(np.float32)
+            P["velocity"][:, 0] = 0.0
+            whole.upload_particles(P)
+            for s in parts:
+                s.upload_particles(P)
+        whole.dispatch_particle(t, True)
+        for s in parts:
+            s.dispatch_particle(t, True)
+        for s in parts:
+            s.sync()
+            assert s.slab_errors() == 0
+        owners = [s.particle_owners() for s in parts]
+        got = slabmod.merge_droplets([s.download_particles() for s in parts], owners)
+        want = whole.download_particles()
+        assert got.tobytes() == want.tobytes(), f"droplets differ after dispatch {k}"
+        who = np.stack(owners).argmax(axis=0)
+        rows_of = np.clip(want["position"][:, 1].astype(np.int64), 0, n - 1)
+        assert all(who[i] == slabmod.owner_of_row(int(rows_of[i]), table) for i in range(count) if want["iters"][i] != 0), "a droplet is not with the slab that holds its row"
+        if owners_before is not None:
+            crossings += int((who != owners_before).sum())
+        owners_before = who
+        for f in (0, 2):
+            full = whole.download(f)
+            sl = np.concatenate([s.download(f) for s in parts], axis=0)
+            assert_bit_equal(sl, full, f"field {f} after dispatch {k}")
+    assert crossings >= 10, f"only {crossings} hand-overs: the test does not exercise migration"
+    for s in parts:
+        s.close()
+    whole.close()
