@@ -406,15 +406,17 @@ def slab_parity(rig, W=1024, rows=512, steps=48):
     return out
 
 
-def droplet_slab_parity(rig, W=512, rows=128, count=128, steps=60):
+def droplet_slab_parity(rig, W=2048, H=2048, count=64, steps=60):
     """The droplet mode on row slabs across processes (CUDA IPC): every rank steps its slab (hand-over of droplets,
     peer atomics on the neighbours' edge texels, image exchanges) AND the whole map on its own GPU; in the sparse regime
     (few droplets, result independent of their order) the droplets it owns, its rows of the heightmap and of the
-    momentum map must equal the whole-map run bit for bit."""
+    momentum map must equal the whole-map run bit for bit.  The map is the same 2048^2 for every N (so the droplets'
+    hashed trajectories are too): 64 droplets that never share a texel in these 60 steps -- with colliding droplets the
+    order of the additions, which is free in the reference as well, shows in the last bit (scripts/drops_slab_debug.py)."""
     import numpy as np
     from hydro_gen_b200 import Context, _lib, slabs
     n = rig.world
-    H = rows * n
+    rows = H // n
 
     def setup(ctx):
         m = ctx.get_map(); m.seed = SEED; m.hmap_dims[0], m.hmap_dims[1] = W, H; ctx.set_map(m)
