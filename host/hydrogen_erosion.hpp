@@ -127,6 +127,19 @@ inline std::vector<float> download(Textures& w, int field) {
     return out;
 }
 
+// CUDA-GL interop with the reference's renderer (library built with -DHG_WITH_GL): the renderer keeps its two
+// gl::Tex_pair objects `heightmap` and `sediment` (src/state.hpp:62-67) and samples their read textures
+// (src/rendering.cpp:103-104).  register_gl once after gen_textures, with the GL names of both textures of each pair
+// (Tex_pair::t1.texture, t2.texture); publish_gl after the frame's erosion steps, with the pairs' read indices
+// (Tex_pair::cntr % 2, src/shaderprogram.cpp:51-60): the fields land in the textures the next draw samples.
+inline void register_gl(Textures& w, const unsigned heightmap_tex[2], const unsigned sediment_tex[2]) {
+    hydrogen_detail::check(hg_register_gl(w.ctx, heightmap_tex, sediment_tex), "register_gl");
+}
+inline void publish_gl(Textures& w, int heightmap_read_idx, int sediment_read_idx) {
+    hydrogen_detail::check(hg_publish_gl(w.ctx, (heightmap_read_idx & 1) | ((sediment_read_idx & 1) << 1)), "publish_gl");
+    hydrogen_detail::check(hg_sync(w.ctx), "publish_gl: sync");      // GL samples after the copies have landed
+}
+
 }  // namespace World
 }  // namespace State
 
