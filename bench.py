@@ -353,6 +353,37 @@ def droplet_config(rig, steps=40, warm=20):
     return out
 
 
+def copy_ceiling(rig, bytes_dir, iters=6):
+    """What the host link allows: the same bytes per step as the e2e leg (bytes_dir up + bytes_dir down, pinned memory,
+    two streams so both directions overlap), with no kernel and no packing at all, all ranks at once.  e2e cannot be
+    faster than this on this host; torch is plumbing here (pinned allocation, streams, events)."""
+    import torch
+    dev = torch.device("cuda", rig.local)
+    n = bytes_dir // 4
+    h_in = torch.empty(n, dtype=torch.float32, pin_memory=True); h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d_in = torch.empty(n, dtype=torch.float32, device=dev); d_out = torch.zeros(n, dtype=torch.float32, device=dev)
+    up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    def once():
+        with torch.cuda.stream(up):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(down):
+            h_out.copy_(d_out, non_blocking=True)
+    once(); torch.cuda.synchronize(dev)
+    rig.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    up.wait_event(e0); down.wait_event(e0)
+    for _ in range(iters):
+        once()
+    torch.cuda.current_stream(dev).wait_stream(up); torch.cuda.current_stream(dev).wait_stream(down)
+    e1.record(torch.cuda.current_stream(dev))
+    torch.cuda.synchronize(dev)
+    ms = rig.reduce(e0.elapsed_time(e1) / iters)
+    rig.barrier()
+    return {"ms_per_step_equivalent": ms, "GBps_per_direction_per_gpu": bytes_dir / ms / 1e6,
+            "what": f"{bytes_dir} B host->device and {bytes_dir} B device->host per GPU, pinned, overlapped on two streams, no kernels; max over ranks"}
+
+
 def contracted_build(args):
     """The same headline workload on the opt-in CONTRACTED build of the library (HG_FMAD=1: -fmad=true, results within
     the north star's tolerance of the reference instead of bit-identical; tests/test_fmad_build.py), in a child process:
@@ -518,6 +549,12 @@ def main():
     halo_errors = rig.reduce(ctx.slab_errors(), "sum")
     for p in pins + pouts:
         p.free()
+    if fields and not args.no_extras:
+        try:
+            e2e["copy_ceiling"] = copy_ceiling(rig, bytes_dir)
+            e2e["fraction_of_copy_ceiling"] = e2e["copy_ceiling"]["ms_per_step_equivalent"] / e2e["ms_per_step"]
+        except Exception as ex:      # the headline must not depend on it
+            e2e["copy_ceiling"] = {"error": repr(ex)[:200]}
     rig.barrier(ctx)
     ctx.close()
 

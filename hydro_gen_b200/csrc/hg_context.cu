@@ -44,6 +44,14 @@ static void free_ctx(hg_ctx* c) {
     if (c->stage_down) cudaFree(c->stage_down);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (int b = 0; b < 2; b++) {
+        if (c->ev_h2d[b]) cudaEventDestroy(c->ev_h2d[b]);
+        if (c->ev_unpacked[b]) cudaEventDestroy(c->ev_unpacked[b]);
+        if (c->ev_packed_b[b]) cudaEventDestroy(c->ev_packed_b[b]);
+        if (c->ev_d2h[b]) cudaEventDestroy(c->ev_d2h[b]);
+    }
     if (c->ev_up) cudaEventDestroy(c->ev_up);
     if (c->ev_comp) cudaEventDestroy(c->ev_comp);
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
@@ -484,18 +492,34 @@ extern "C" int hg_mass(hg_ctx* c, double out5[5]) {
 // for ev_packed; staging buffers are reused in stream order.
 static int ensure_host_pipe(hg_ctx* c) {
     if (c->stage_up) return HG_OK;
-    const size_t bytes = (size_t)3 * c->g.rows * c->g.W * 4 * sizeof(float);
+    const size_t bytes = (size_t)2 * 3 * c->g.rows * c->g.W * 4 * sizeof(float);
     HG_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     HG_CUDA(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+    HG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    HG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     HG_CUDA(cudaMalloc(&c->stage_up, bytes));
     HG_CUDA(cudaMalloc(&c->stage_down, bytes));
     HG_CUDA(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
     HG_CUDA(cudaEventCreateWithFlags(&c->ev_comp, cudaEventDisableTiming));
     HG_CUDA(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     HG_CUDA(cudaEventCreate(&c->ev_down));
+    for (int b = 0; b < 2; b++) {
+        HG_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[b], cudaEventDisableTiming));
+        HG_CUDA(cudaEventCreateWithFlags(&c->ev_unpacked[b], cudaEventDisableTiming));
+        HG_CUDA(cudaEventCreateWithFlags(&c->ev_packed_b[b], cudaEventDisableTiming));
+        HG_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[b], cudaEventDisableTiming));
+    }
     return HG_OK;
 }
 
+// One Erosion::dispatch_grid from HOST images to HOST images.  Call k (staging buffers k & 1):
+//   h2d_stream : [unpack(k-2) done with the buffer]      copy H, F, S into stage_up
+//   up_stream  : [copies(k) done] [everything earlier on the main stream done] [pack(k-1) done with the planes]   unpack
+//   stream     : [unpack(k) done]                         fused step + halo exchange
+//   down_stream: [step(k) done] [copies-out(k-2) done with the buffer]   pack into stage_down
+//   d2h_stream : [pack(k) done]                           copy H, F, S out
+// so the two PCIe directions run back to back without waiting for a kernel of the neighbouring call: the period of
+// the pipeline is the longer of the two copies (bench.py: e2e against e2e.copy_ceiling).
 extern "C" int hg_step_host_async(hg_ctx* c, const float* in_h, const float* in_f, const float* in_s,
                                   float* out_h, float* out_f, float* out_s) {
     HG_CHECK_CTX(c);
@@ -508,21 +532,30 @@ extern "C" int hg_step_host_async(hg_ctx* c, const float* in_h, const float* in_
     float* out[3] = {out_h, out_f, out_s};
     const size_t n = (size_t)c->g.rows * c->g.W;            // texels per field
     const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-    // uploads: everything already enqueued on the main stream (a previous plain dispatch, an
-    // upload ...) must be done with the planes before they are overwritten
+    const int b = (int)(c->host_pipe_calls & 1u);
+    const bool reuse = c->host_pipe_calls >= 2;              // the buffers of call k-2 are in flight
+    float* const sup = c->stage_up + (size_t)b * 3 * n * 4;
+    float* const sdn = c->stage_down + (size_t)b * 3 * n * 4;
+    // copies in
+    if (reuse) HG_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_unpacked[b], 0));
+    for (int k = 0; k < 3; k++)
+        HG_CUDA(cudaMemcpyAsync(sup + (size_t)k * n * 4, in[k], n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    HG_CUDA(cudaEventRecord(c->ev_h2d[b], c->h2d_stream));
+    // unpack: the planes must be free -- everything already enqueued on the main stream (a previous plain dispatch, an
+    // upload ...) and the pack of the previous call
     HG_CUDA(cudaEventRecord(c->ev_comp, c->stream));
     HG_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_comp, 0));
-    for (int k = 0; k < 3; k++)
-        HG_CUDA(cudaMemcpyAsync(c->stage_up + (size_t)k * n * 4, in[k], n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->up_stream));
+    HG_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_h2d[b], 0));
     if (c->host_pipe_busy) HG_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_packed, 0));
     for (int k = 0; k < 3; k++) {
         Chan4 ch; int synth;
         rc = field_channels(c, fields[k], &ch, &synth, true);
         if (rc) return rc;
-        k_unpack<<<blocks, 256, 0, c->up_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<const float4*>(c->stage_up + (size_t)k * n * 4));
+        k_unpack<<<blocks, 256, 0, c->up_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<const float4*>(sup + (size_t)k * n * 4));
         HG_LAUNCH_CHECK(c);
     }
     HG_CUDA(cudaEventRecord(c->ev_up, c->up_stream));
+    HG_CUDA(cudaEventRecord(c->ev_unpacked[b], c->up_stream));
     // the step
     HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
     rc = hg_launch_fused_step(c);
@@ -530,20 +563,26 @@ extern "C" int hg_step_host_async(hg_ctx* c, const float* in_h, const float* in_
     rc = hg_slab_exchange(c);
     if (rc) return rc;
     HG_CUDA(cudaEventRecord(c->ev_comp, c->stream));
-    // pack + downloads
+    // pack
     HG_CUDA(cudaStreamWaitEvent(c->down_stream, c->ev_comp, 0));
+    if (reuse) HG_CUDA(cudaStreamWaitEvent(c->down_stream, c->ev_d2h[b], 0));
     for (int k = 0; k < 3; k++) {
         Chan4 ch; int synth;
         rc = field_channels(c, fields[k], &ch, &synth, false);
         if (rc) return rc;
-        k_pack<<<blocks, 256, 0, c->down_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<float4*>(c->stage_down + (size_t)k * n * 4), synth);
+        k_pack<<<blocks, 256, 0, c->down_stream>>>(ch, c->g.W, c->g.pitch, 0, c->g.rows, reinterpret_cast<float4*>(sdn + (size_t)k * n * 4), synth);
         HG_LAUNCH_CHECK(c);
     }
     HG_CUDA(cudaEventRecord(c->ev_packed, c->down_stream));
+    HG_CUDA(cudaEventRecord(c->ev_packed_b[b], c->down_stream));
+    // copies out
+    HG_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_packed_b[b], 0));
     for (int k = 0; k < 3; k++)
-        HG_CUDA(cudaMemcpyAsync(out[k], c->stage_down + (size_t)k * n * 4, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->down_stream));
-    HG_CUDA(cudaEventRecord(c->ev_down, c->down_stream));
+        HG_CUDA(cudaMemcpyAsync(out[k], sdn + (size_t)k * n * 4, n * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+    HG_CUDA(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
+    HG_CUDA(cudaEventRecord(c->ev_down, c->d2h_stream));
     c->host_pipe_busy = true;
+    c->host_pipe_calls++;
     return HG_OK;
 }
 
@@ -554,6 +593,8 @@ extern "C" int hg_sync(hg_ctx* c) {
     HG_CUDA(cudaStreamSynchronize(c->stream));
     if (c->up_stream) HG_CUDA(cudaStreamSynchronize(c->up_stream));
     if (c->down_stream) HG_CUDA(cudaStreamSynchronize(c->down_stream));
+    if (c->h2d_stream) HG_CUDA(cudaStreamSynchronize(c->h2d_stream));
+    if (c->d2h_stream) HG_CUDA(cudaStreamSynchronize(c->d2h_stream));
     return hg_slab_check_sticky(c);
 }
 extern "C" int hg_set_stream(hg_ctx* c, void* s) {

@@ -111,10 +111,14 @@ struct hg_ctx {
     float* staging;            // device staging for RGBA pack/unpack
     size_t staging_elems;
     // pipelined host step (hg_step_host_async): copy streams, full-size staging, ordering events
-    cudaStream_t up_stream, down_stream;
-    float* stage_up;           // 3 fields x rows x W x 4 floats (H, F, S as RGBA32F)
+    // five streams: host->device copies | unpack kernels | (the step, on `stream`) | pack kernels | device->host copies;
+    // the staging images are double-buffered (call k uses buffer k & 1), so a copy of call k+1 never waits for a kernel of call k
+    cudaStream_t up_stream, down_stream, h2d_stream, d2h_stream;
+    float* stage_up;           // 2 buffers x 3 fields x rows x W x 4 floats (H, F, S as RGBA32F)
     float* stage_down;
     cudaEvent_t ev_up, ev_comp, ev_packed, ev_down;
+    cudaEvent_t ev_h2d[2], ev_unpacked[2], ev_packed_b[2], ev_d2h[2];
+    unsigned host_pipe_calls;  // hg_step_host_async calls so far
     bool host_pipe_busy;       // ev_packed / ev_down have been recorded at least once
 
     // CUDA-GL interop (HG_WITH_GL): registered textures [heightmap | sediment][index in the Tex_pair], staging image
