@@ -117,6 +117,8 @@ static int create_impl(hg_ctx* c) {
             HG_CUDA(cudaMemsetAsync(c->pa, 0, (size_t)4 * c->g.plane_elems * sizeof(float4), c->stream));
             HG_CUDA(cudaMalloc(&c->p_own, c->particle_count));
             HG_CUDA(cudaMemsetAsync(c->p_own, 0, c->particle_count, c->stream));
+            int rco = hg_particle_order_alloc(c, (1 << 21) + 1);
+            if (rco) return rco;
         }
     }
     HG_CUDA(cudaStreamSynchronize(c->stream));
@@ -456,6 +458,7 @@ extern "C" int hg_slab_particle_owners(hg_ctx* c, unsigned char* dst, uint32_t c
     if (!c->p_own) { memset(dst, 1, count); return HG_OK; }      // a whole map owns all its droplets
     HG_CUDA(cudaMemcpyAsync(dst, c->p_own, count, cudaMemcpyDeviceToHost, c->stream));
     HG_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t k = 0; k < count; k++) dst[k] = dst[k] ? 1 : 0;      // 2 = handed over during the last erode pass: this slab holds its state
     return HG_OK;
 }
 

@@ -195,6 +195,7 @@ int hg_launch_rain(hg_ctx* c, float time);
 int hg_launch_heightmap(hg_ctx* c);
 int hg_launch_particle_spawn(hg_ctx* c, float time, int should_rain);   // slabs: respawn + hand-over before the move
 int hg_particle_own_init(hg_ctx* c);
+int hg_particle_order_alloc(hg_ctx* c, int nbins);
 int hg_slab_push_images(hg_ctx* c);   // droplet slabs: edge rows of the H and M images to the neighbours' ghost rows + signal
 int hg_launch_particle_move(hg_ctx* c, float time, int should_rain);
 int hg_launch_particle_erode(hg_ctx* c);

@@ -50,15 +50,20 @@ __device__ __forceinline__ int slab_of_row(const PSlabs& S, int y) {
     }
     return k;
 }
-// hand droplet `id` (state p) to the slab that holds its position; returns true if it left this slab
-__device__ __forceinline__ void slab_store_droplet(const PSlabs& S, uint32_t id, const hg_particle& p, int H) {
+// Store droplet `id` (state p) with the slab that holds its position.  Ownership byte: 0 = another slab's, 1 = mine,
+// 2 = handed to me during an erode pass: mine from the NEXT dispatch on (its spawn kernel promotes 2 to 1).  Without the
+// pending state a slab whose erode kernel starts after its neighbour's has finished would erode the droplets it has just
+// been handed a second time (found by running the slab test under compute-sanitizer, which delays kernels).  Hand-overs
+// of the spawn pass take effect at once: the receiving spawn kernel has nothing to do for a freshly spawned droplet,
+// and the move pass runs after an all-rank generation.
+__device__ __forceinline__ void slab_store_droplet(const PSlabs& S, uint32_t id, const hg_particle& p, int H, unsigned char marker) {
     int y = (int)p.position[1];
     y = min(max(y, 0), H - 1);
     const int o = slab_of_row(S, y);
     S.parts[o][id] = p;
     if (o != S.me) {
         __threadfence_system();          // the element before the ownership byte
-        S.own[o][id] = 1;
+        S.own[o][id] = marker;
         S.own[S.me][id] = 0;
     }
 }
@@ -98,7 +103,10 @@ struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t*
 // anywhere on the map and must be with its new owner BEFORE it moves (the move samples the terrain around it).
 __global__ void __launch_bounds__(128) k_particle_spawn(PSlabs S, int H, hg_erosion_data set, hg_map_settings_data map_set, uint32_t count, float time, int should_rain) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= count || !S.own[S.me][id] || !should_rain) return;       // without rain the shader returns before it stores anything
+    if (id >= count) return;
+    unsigned char mine = S.own[S.me][id];
+    if (mine == 2) { S.own[S.me][id] = 1; mine = 1; }                  // handed over during the last erode pass
+    if (mine != 1 || !should_rain) return;                             // without rain the shader returns before it stores anything
     hg_particle p = S.parts[S.me][id];
     if (!(p.iters == 0 || p.to_kill)) return;
 #pragma unroll
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(128) k_particle_spawn(PSlabs S, int H, hg_eros
     p.velocity[0] = 0.0f; p.velocity[1] = 0.0f;
     p.volume = set.init_volume;
     p.iters = 1;
-    slab_store_droplet(S, id, p, H);
+    slab_store_droplet(S, id, p, H, 1);
 }
 
 // particle.glsl:64-136
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
     if (A.order) id = A.order[id];      // thread k takes the k-th droplet in tile order; the droplet keeps its id (spawn hash)
-    if (A.own && !A.own[id]) return;    // slabs: another rank's droplet
+    if (A.own && A.own[id] != 1) return;    // slabs: another rank's droplet
     hg_particle p = A.particles[id];
     if (p.iters == 0 && !should_rain) return;
 #pragma unroll
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = id < count;
     if (live && A.order) id = A.order[id];
-    if (SLAB) live = live && S.own[S.me][id];
+    if (SLAB) live = live && S.own[S.me][id] == 1;      // not 2: a droplet handed over during this very pass has been eroded by its old owner
     hg_particle part = {};
     if (live) part = A.particles[id];
     live = live && part.iters != 0;
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
         warp_corner_add(hp, mp, v, act);
     }
     if (live) {
-        if (SLAB) slab_store_droplet(S, id, part, d.H);      // stays, or goes to the slab it drifted into
+        if (SLAB) slab_store_droplet(S, id, part, d.H, 2);      // stays, or goes to the slab it drifted into (from the next dispatch on)
         else A.particles[id] = part;
     }
 }
@@ -393,9 +401,16 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
 // is rebuilt only every p_rebin_period dispatches.
 constexpr int kScanBlock = 2048;      // bins per scan block (512 threads x 4)
 struct BinDom { int shift, bx, by; };
-__global__ void __launch_bounds__(256) k_bin_keys(const hg_particle* parts, uint32_t count, BinDom b, uint32_t* keys, uint32_t* hist) {
+// own: null, or the slab's ownership bytes: another rank's droplets go into one extra bin behind all the others
+__global__ void __launch_bounds__(256) k_bin_keys(const hg_particle* parts, uint32_t count, BinDom b, uint32_t* keys, uint32_t* hist, const unsigned char* own) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
+    if (own && own[id] != 1) {
+        const uint32_t last = (uint32_t)b.bx * (uint32_t)b.by;
+        keys[id] = last;
+        atomicAdd(hist + last, 1u);
+        return;
+    }
     const float2 pos = *reinterpret_cast<const float2*>(parts[id].position);
     int cx = (int)fminf(fmaxf(pos.x, 0.0f), 1e9f) >> b.shift, cy = (int)fminf(fmaxf(pos.y, 0.0f), 1e9f) >> b.shift;
     cx = min(cx, b.bx - 1); cy = min(cy, b.by - 1);
@@ -456,6 +471,21 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* keys, uint3
 
 }  // namespace
 
+// scratch of the processing order; a droplet SLAB allocates it for the largest bin count at create time (no allocation
+// may happen between two exchange generations)
+int hg_particle_order_alloc(hg_ctx* c, int nbins) {
+    if (!c->p_order) {
+        HG_CUDA(cudaMalloc(&c->p_order, (size_t)c->particle_count * sizeof(uint32_t)));
+        HG_CUDA(cudaMalloc(&c->p_keys, (size_t)c->particle_count * sizeof(uint32_t)));
+    }
+    if (c->p_bins_cap < nbins) {
+        if (c->p_hist) HG_CUDA(cudaFree(c->p_hist));
+        HG_CUDA(cudaMalloc(&c->p_hist, ((size_t)nbins + 1100) * sizeof(uint32_t)));
+        c->p_bins_cap = nbins;
+    }
+    return HG_OK;
+}
+
 // (Re)build the processing order from the droplets' current positions.
 static int rebuild_order(hg_ctx* c, uint32_t count) {
     int hx = c->map.hmap_dims[0] > 0 ? c->map.hmap_dims[0] : c->g.W, hy = c->map.hmap_dims[1] > 0 ? c->map.hmap_dims[1] : c->g.H;
@@ -463,19 +493,13 @@ static int rebuild_order(hg_ctx* c, uint32_t count) {
     if (hy > c->g.H) hy = c->g.H;
     BinDom b{0, hx, hy};
     while ((long long)b.bx * b.by > (1LL << 21)) { b.shift++; b.bx = (hx + (1 << b.shift) - 1) >> b.shift; b.by = (hy + (1 << b.shift) - 1) >> b.shift; }
-    const int nbins = b.bx * b.by, nblocks = (nbins + kScanBlock - 1) / kScanBlock;
-    if (!c->p_order) {
-        HG_CUDA(cudaMalloc(&c->p_order, (size_t)c->particle_count * sizeof(uint32_t)));
-        HG_CUDA(cudaMalloc(&c->p_keys, (size_t)c->particle_count * sizeof(uint32_t)));
-    }
-    if (c->p_bins_cap < nbins) {
-        if (c->p_hist) HG_CUDA(cudaFree(c->p_hist));
-        HG_CUDA(cudaMalloc(&c->p_hist, ((size_t)nbins + 1024) * sizeof(uint32_t)));
-        c->p_bins_cap = nbins;
-    }
-    uint32_t* sums = c->p_hist + nbins;
+    const int nbins = b.bx * b.by + 1;      // + the bin of the droplets another slab owns
+    const int nblocks = (nbins + kScanBlock - 1) / kScanBlock;
+    int rca = hg_particle_order_alloc(c, nbins);
+    if (rca) return rca;
+    uint32_t* sums = c->p_hist + c->p_bins_cap;
     HG_CUDA(cudaMemsetAsync(c->p_hist, 0, (size_t)nbins * sizeof(uint32_t), c->stream));
-    k_bin_keys<<<(count + 255) / 256, 256, 0, c->stream>>>(c->particles, count, b, c->p_keys, c->p_hist);
+    k_bin_keys<<<(count + 255) / 256, 256, 0, c->stream>>>(c->particles, count, b, c->p_keys, c->p_hist, (c->p_own && c->peers_connected) ? c->p_own : nullptr);
     HG_LAUNCH_CHECK(c);
     k_bin_scan1<<<nblocks, 512, 0, c->stream>>>(c->p_hist, nbins, sums);
     HG_LAUNCH_CHECK(c);
@@ -522,13 +546,14 @@ int hg_launch_particle_move(hg_ctx* c, float time, int should_rain) {
     if (rc) return rc;
     const bool slabs = droplet_slabs(c);
     // processing order: rebuilt when it has aged; a fresh context (nothing spawned yet) moves in id order and sorts
-    // after the move, when the droplets have their spawn positions (hg_launch_particle_erode).  Slabs process their
-    // droplets in id order (ownership changes every step).
-    if (!slabs && c->p_rebin_period > 0 && c->p_order_valid && ++c->p_rebin_age >= c->p_rebin_period) {
+    // after the move, when the droplets have their spawn positions (hg_launch_particle_erode).  A slab's set of
+    // droplets changes every step (hand-overs), so it sorts the droplets it owns before every move; the others
+    // land in a bin of their own at the end and are skipped by their ownership byte.
+    if (c->p_rebin_period > 0 && (slabs || (c->p_order_valid && ++c->p_rebin_age >= c->p_rebin_period))) {
         rc = rebuild_order(c, count);
         if (rc) return rc;
     }
-    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, (!slabs && c->p_order_valid) ? c->p_order : nullptr, slabs ? c->p_own : nullptr};
+    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, c->p_order_valid ? c->p_order : nullptr, slabs ? c->p_own : nullptr};
     k_particle_move<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, c->erosion, c->map, A, count, time, should_rain);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
@@ -547,7 +572,7 @@ int hg_launch_particle_erode(hg_ctx* c) {
         if (rc) return rc;
     }
     ErodeArgs A;
-    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = (!slabs && c->p_order_valid) ? c->p_order : nullptr;
+    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = c->p_order_valid ? c->p_order : nullptr;
     if (slabs) {
         k_particle_erode<true><<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count, make_pslabs(c));
     } else {
@@ -590,5 +615,9 @@ int hg_preload_particle_kernels(void) {
     HG_CUDA(cudaFuncGetAttributes(&a, k_particle_erode<false>));
     HG_CUDA(cudaFuncGetAttributes(&a, k_own_init));
     HG_CUDA(cudaFuncGetAttributes(&a, k_own_from_positions));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_bin_keys));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_bin_scan1));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_bin_scan2));
+    HG_CUDA(cudaFuncGetAttributes(&a, k_bin_scatter));
     return HG_OK;
 }
