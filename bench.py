@@ -399,6 +399,32 @@ def contracted_build(args):
         return {"error": repr(e)[:300]}
 
 
+def droplet_slabs_config(rig, steps=40, warm=20):
+    """BASELINE config 4 on N GPUs (the reference is single-GPU; SURVEY.md §8e lists sharded droplets under "next"): the
+    same 4 Mi droplets on 8192^2, hmap_dims = map, row slabs of 8192/N rows, droplets owned by the slab that holds them,
+    hand-over and peer atomics over NVLink.  Device-timed, max over ranks."""
+    from hydro_gen_b200 import Context, _lib, slabs
+    N, COUNT, n = 8192, 4 * 1024 * 1024, rig.world
+    rows = N // n
+    ctx = Context(N, N, particle_count=COUNT, erosion_type=_lib.HG_PARTICLES, device=rig.local, row0=rig.rank * rows, rows=rows)
+    slabs.connect_ring(ctx, rig.dist, n, rig.rank)
+    m = ctx.get_map(); m.seed = SEED; m.hmap_dims[0], m.hmap_dims[1] = N, N; ctx.set_map(m)
+    ctx.gen_heightmap()
+    rig.barrier(ctx)
+    ctx.run(warm, DT_TIME, DT_TIME, True)
+    rig.barrier(ctx)
+    ctx.timer_start()
+    ctx.run(steps, (warm + 1) * DT_TIME, DT_TIME, True)
+    ms = rig.reduce(ctx.timer_stop() / steps)
+    owned = rig.reduce(float(ctx.particle_owners().sum()), "sum")
+    errs = rig.reduce(ctx.slab_errors(), "sum")
+    rig.barrier(ctx)
+    ctx.close()
+    return {"workload": f"Erosion::dispatch_particle, 4194304 droplets on 8192x8192 over {n} row slabs of {rows} rows, hmap_dims = map",
+            "ms_per_dispatch": ms, "Mdroplet_steps_per_s": COUNT / ms / 1e3, "steps": steps, "droplets_with_an_owner": owned, "halo_errors": errs,
+            "speedup_note": "one GPU: droplets_8192_4Mi.hmap_dims_8192 of the N=1 line"}
+
+
 def slab_parity(rig, W=1024, rows=512, steps=48):
     """scripts/mgpu_check.py inside the bench: every rank steps its slab of a W x (rows * N) map with NVLink halo
     pushes (CUDA IPC between the processes) AND the whole map on its own GPU, and compares its rows bit for bit;
@@ -576,6 +602,8 @@ def main():
             line["droplets_8192_4Mi"] = droplet_config(rig)
         else:
             line["slab_parity"] = slab_parity(rig)
+            if 8192 % (8 * n) == 0:
+                line["droplets_8192_4Mi_slabs"] = droplet_slabs_config(rig)
             if 16384 % (8 * n) == 0:
                 r3 = 16384 // n
                 c3 = make_grid(rig, 16384, r3)

@@ -97,7 +97,7 @@ __device__ __forceinline__ float prand(float px, float py) {
     return hg_fract(1e4f * hg_sinf(17.0f * px + py * 0.1f) * (0.1f + fabsf(hg_sinf(py * 13.0f + px))));
 }
 
-struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t* order; const unsigned char* own; };
+struct MoveArgs { const float4 *ha, *ma; hg_particle* particles; const uint32_t* order; const unsigned char* own; const uint32_t* n_valid; };
 
 // The spawn half of particle.glsl:64-90 on its own, for slabs: a droplet that (re)spawns gets its hashed position
 // anywhere on the map and must be with its new owner BEFORE it moves (the move samples the terrain around it).
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(128) k_particle_move(PDom d, HgStepParams P, h
                                                        MoveArgs A, uint32_t count, float time, int should_rain) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
+    if (A.order && id >= *A.n_valid) return;      // a slab's order holds only the droplets it owns
     if (A.order) id = A.order[id];      // thread k takes the k-th droplet in tile order; the droplet keeps its id (spawn hash)
     if (A.own && A.own[id] != 1) return;    // slabs: another rank's droplet
     hg_particle p = A.particles[id];
@@ -294,7 +295,7 @@ __device__ __forceinline__ void warp_erode(float* addr, float eroded, bool on, f
     }
 }
 
-struct ErodeArgs : ErodeImages { hg_particle* particles; const uint32_t* order; };
+struct ErodeArgs : ErodeImages { hg_particle* particles; const uint32_t* order; const uint32_t* n_valid; };
 
 // the heightmap / momentum texel (x, y) wherever it lives: this slab's images, or the owning rank's through its peer pointer
 template <bool SLAB>
@@ -310,6 +311,7 @@ template <bool SLAB>
 __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, ErodeArgs A, uint32_t count, const __grid_constant__ PSlabs S) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = id < count;
+    if (live && A.order) live = id < *A.n_valid;
     if (live && A.order) id = A.order[id];
     if (SLAB) live = live && S.own[S.me][id] == 1;      // not 2: a droplet handed over during this very pass has been eroded by its old owner
     hg_particle part = {};
@@ -401,16 +403,11 @@ __global__ void __launch_bounds__(128) k_particle_erode(PDom d, HgStepParams P, 
 // is rebuilt only every p_rebin_period dispatches.
 constexpr int kScanBlock = 2048;      // bins per scan block (512 threads x 4)
 struct BinDom { int shift, bx, by; };
-// own: null, or the slab's ownership bytes: another rank's droplets go into one extra bin behind all the others
+// own: null, or the slab's ownership bytes: another rank's droplets are left out of the order
 __global__ void __launch_bounds__(256) k_bin_keys(const hg_particle* parts, uint32_t count, BinDom b, uint32_t* keys, uint32_t* hist, const unsigned char* own) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= count) return;
-    if (own && own[id] != 1) {
-        const uint32_t last = (uint32_t)b.bx * (uint32_t)b.by;
-        keys[id] = last;
-        atomicAdd(hist + last, 1u);
-        return;
-    }
+    if (own && own[id] != 1) { keys[id] = 0xffffffffu; return; }      // not in the order at all
     const float2 pos = *reinterpret_cast<const float2*>(parts[id].position);
     int cx = (int)fminf(fmaxf(pos.x, 0.0f), 1e9f) >> b.shift, cy = (int)fminf(fmaxf(pos.y, 0.0f), 1e9f) >> b.shift;
     cx = min(cx, b.bx - 1); cy = min(cy, b.by - 1);
@@ -461,10 +458,14 @@ __global__ void __launch_bounds__(1024) k_bin_scan2(uint32_t* sums, int n) {
     __syncthreads();
     if ((int)threadIdx.x < n) sums[threadIdx.x] = wsum[warp] + incl - v;
 }
-__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* keys, uint32_t count, uint32_t* hist, const uint32_t* sums, uint32_t* order) {
+// last_bin: an empty bin behind all the others; its offset after the scan is the number of droplets in the order
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint32_t* keys, uint32_t count, uint32_t* hist, const uint32_t* sums, uint32_t* order,
+                                                     uint32_t last_bin, uint32_t* n_valid) {
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0) *n_valid = hist[last_bin] + sums[last_bin / kScanBlock];
     if (id >= count) return;
     const uint32_t key = keys[id];
+    if (key == 0xffffffffu) return;
     const uint32_t pos = atomicAdd(hist + key, 1u) + sums[key / kScanBlock];
     order[pos] = id;
 }
@@ -493,7 +494,7 @@ static int rebuild_order(hg_ctx* c, uint32_t count) {
     if (hy > c->g.H) hy = c->g.H;
     BinDom b{0, hx, hy};
     while ((long long)b.bx * b.by > (1LL << 21)) { b.shift++; b.bx = (hx + (1 << b.shift) - 1) >> b.shift; b.by = (hy + (1 << b.shift) - 1) >> b.shift; }
-    const int nbins = b.bx * b.by + 1;      // + the bin of the droplets another slab owns
+    const int nbins = b.bx * b.by + 1;      // + an empty last bin whose offset is the number of droplets in the order (sums[1050])
     const int nblocks = (nbins + kScanBlock - 1) / kScanBlock;
     int rca = hg_particle_order_alloc(c, nbins);
     if (rca) return rca;
@@ -505,7 +506,7 @@ static int rebuild_order(hg_ctx* c, uint32_t count) {
     HG_LAUNCH_CHECK(c);
     k_bin_scan2<<<1, 1024, 0, c->stream>>>(sums, nblocks);
     HG_LAUNCH_CHECK(c);
-    k_bin_scatter<<<(count + 255) / 256, 256, 0, c->stream>>>(c->p_keys, count, c->p_hist, sums, c->p_order);
+    k_bin_scatter<<<(count + 255) / 256, 256, 0, c->stream>>>(c->p_keys, count, c->p_hist, sums, c->p_order, (uint32_t)(nbins - 1), sums + 1050);
     HG_LAUNCH_CHECK(c);
     c->p_order_valid = true;
     c->p_rebin_age = 0;
@@ -553,7 +554,7 @@ int hg_launch_particle_move(hg_ctx* c, float time, int should_rain) {
         rc = rebuild_order(c, count);
         if (rc) return rc;
     }
-    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, c->p_order_valid ? c->p_order : nullptr, slabs ? c->p_own : nullptr};
+    MoveArgs A{hg_pa_h(c, 1), hg_pa_m(c, 1), c->particles, c->p_order_valid ? c->p_order : nullptr, slabs ? c->p_own : nullptr, c->p_order_valid ? c->p_hist + c->p_bins_cap + 1050 : nullptr};
     k_particle_move<<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, c->erosion, c->map, A, count, time, should_rain);
     HG_LAUNCH_CHECK(c);
     return HG_OK;
@@ -572,7 +573,7 @@ int hg_launch_particle_erode(hg_ctx* c) {
         if (rc) return rc;
     }
     ErodeArgs A;
-    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = c->p_order_valid ? c->p_order : nullptr;
+    A.ha = hg_pa_h(c, 1); A.ma = hg_pa_m(c, 1); A.particles = c->particles; A.order = c->p_order_valid ? c->p_order : nullptr; A.n_valid = c->p_order_valid ? c->p_hist + c->p_bins_cap + 1050 : nullptr;
     if (slabs) {
         k_particle_erode<true><<<(count + 127) / 128, 128, 0, c->stream>>>(d, c->sp, A, count, make_pslabs(c));
     } else {
