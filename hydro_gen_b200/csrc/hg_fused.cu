@@ -175,7 +175,7 @@ template <int NT> struct FusedSmem {
     static constexpr size_t BYTES = (BARS + 4) * sizeof(float);
 };
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool DROPS = false>
 __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
     // Dynamic shared memory is the kernel's only shared allocation, so it starts at the CTA's window
     // base (1 KiB aligned); the TMA destination needs 128 bytes.  (Rounding the pointer up at run
@@ -196,15 +196,16 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     // element offset of (row i, column x) in a plane, advanced by one row per iteration
     unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
     const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;      // plane row of iteration i_begin
-    constexpr unsigned BOX_BYTES = (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
+    constexpr unsigned BOX_BYTES = DROPS ? (unsigned)(HGF_RAW_LD(NT) * 4 * sizeof(float)) : (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
     const int bx0 = x0 - 2;      // box start column: a multiple of 4 (TMA needs a 16-byte aligned start)
+#define HG_TMA_ROW1(dst, bar, row) (DROPS ? tma_load_3d((dst), &tmap, (bar), 0, bx0, (row)) : tma_load_3d((dst), &tmap, (bar), bx0, (row), 0))
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&bars[0], BOX_BYTES);
-        tma_load_3d(smb, &tmap, &bars[0], bx0, ly0, 0);
+        HG_TMA_ROW1(smb, &bars[0], ly0);
     }
     __syncthreads();
     HgCol c;
@@ -218,10 +219,10 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
         const int rel = i - pl.i_begin;                                                                              \
         if (tid == 0 && i < pl.i_end) {                                                                              \
             mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
-            tma_load_3d(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &tmap, &bars[(rel + 1) & 1], bx0, ly0 + rel + 1, 0); \
+            HG_TMA_ROW1(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &bars[(rel + 1) & 1], ly0 + rel + 1);         \
         }                                                                                                            \
         mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
-        hg_fused_iter<NT, FREEFLAG>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        hg_fused_iter<NT, FREEFLAG, HGF_ALL, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
         __syncthreads();                                                                                             \
     }
     for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW(false)
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(NT, MINB) k_fused_step(const __grid_constant__
     for (; i <= pl.free_hi; i++, off += pitch) HG_ROW(true)
     for (; i <= pl.i_end; i++, off += pitch) HG_ROW(false)
 #undef HG_ROW
+#undef HG_TMA_ROW1
 }
 
 // Warp-specialised form of the same step: a CTA of 2*NT threads, threads [0, NT) run the
@@ -534,7 +536,7 @@ static int make_tmap_aos(hg_ctx* c, const float4* image, int box_cols, CUtensorM
 }
 
 // NT threads per CTA; seg rows per CTA.
-template <int NT, int MINB>
+template <int NT, int MINB, bool DROPS = false>
 static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     HgFusedK K = K0;
     K.nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
@@ -543,14 +545,14 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     constexpr size_t smem = FusedSmem<NT>::BYTES;
     static bool attr_set[HG_MAX_DEVICES] = {};      // the attribute is per device (one process may drive several GPUs)
     if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
-        HG_CUDA(cudaFuncSetAttribute(k_fused_step<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA(cudaFuncSetAttribute(k_fused_step<NT, MINB, DROPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
+    int rc = DROPS ? make_tmap_aos(c, reinterpret_cast<const float4*>(K.ha_src), HGF_RAW_LD(NT), &tmap) : make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
-    k_fused_step<NT, MINB><<<K.nstrips * nseg, NT, smem, c->stream>>>(K, tmap);
+    k_fused_step<NT, MINB, DROPS><<<K.nstrips * nseg, NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
@@ -692,7 +694,7 @@ static int launch_fused(hg_ctx* c, bool drops) {
     static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2};
     static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8};
     int v = c->tune_variant >= 0 && c->tune_variant < NVAR ? c->tune_variant : HG_FUSED_DEFAULT_VARIANT;
-    if (drops) v = 5;
+    if (drops) v = c->tune_drops_variant == 1 ? 3 : 5;      // HG_DROPS_VARIANT=1: one warp group of 224 threads runs every stage
     const bool two_lane = v >= 10;
     const int NT = nt_of[v];
     const int strip_w = two_lane ? 2 * HGF2_HALF(NT) : NT - 2 * HGF_HX;      // owned columns per CTA
@@ -765,7 +767,7 @@ static int launch_fused(hg_ctx* c, bool drops) {
     case 0: rc = launch_main<128, 4>(c, K, seg, c->ri[0]); break;
     case 1: rc = launch_main<128, 3>(c, K, seg, c->ri[0]); break;
     case 2: rc = launch_main<192, 2>(c, K, seg, c->ri[0]); break;
-    case 3: rc = launch_main<224, 2>(c, K, seg, c->ri[0]); break;
+    case 3: rc = drops ? launch_main<224, 3, true>(c, K, seg, c->ri[0]) : launch_main<224, 2>(c, K, seg, c->ri[0]); break;
     case 4: rc = launch_main<224, 1>(c, K, seg, c->ri[0]); break;
     case 5: rc = drops ? launch_ws<128, 3, 72, 88, true>(c, K, seg, c->ri[0]) : launch_ws<128, 3, 72, 88>(c, K, seg, c->ri[0]); break;
     case 6: rc = launch_ws<128, 2, 96, 128>(c, K, seg, c->ri[0]); break;

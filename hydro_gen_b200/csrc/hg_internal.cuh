@@ -99,6 +99,7 @@ struct hg_ctx {
     unsigned* far_list;        // cells whose back-trace left the on-chip window this step (lazy)
     int far_parity;
     int tune_variant;          // CTA shape of the fused kernel; -1 = default (HG_FUSED_VARIANT env at create)
+    int tune_drops_variant;    // droplet-mode tail: 0 = warp-specialised (default), 1 = one warp group of 224 threads (HG_DROPS_VARIANT)
     int tune_seg;              // rows per CTA of the fused kernel; 0 = automatic (HG_FUSED_SEG env at create)
     // balanced partition of the fused step (hg_fused.cu, k_plan_segments): two plans (this step's / next step's), the
     // durations the CTAs reported, which plan is current; no_balance = HG_FUSED_BALANCE=0

@@ -220,3 +220,58 @@ def test_droplet_slabs_match_whole_map(built):
     for s in parts:
         s.close()
     whole.close()
+
+
+def test_refresh_halo_after_plain_uploads(built):
+    """hg_upload on a connected slab replaces the owned rows only; hg_slab_refresh_halo (collective) re-fills the ghost
+    rows from the neighbours, after which the slabs reproduce the whole-map run bit for bit without any
+    hg_slab_set_ghost (plain uploads left stale ghost rows)."""
+    n = 256
+    w = wet_world(n, 300)
+    whole = Context(n)
+    copy_state(w, whole)
+    cuts = [0, 64, 200, 256]
+    slabs = [Context(n, n, row0=cuts[i], rows=cuts[i + 1] - cuts[i]) for i in range(3)]
+    for i, s in enumerate(slabs):
+        s.connect_local(slabs, i)
+    for name in ("heightmap", "flux", "sediment"):
+        full = w.get(FIELDS[name])
+        for i, s in enumerate(slabs):
+            s.upload(FIELDS[name], full[cuts[i]:cuts[i + 1]])
+    for s in slabs:
+        s.refresh_halo()
+    for _ in range(5):
+        whole.dispatch_grid()
+        for s in slabs:
+            s.dispatch_grid()
+    for s in slabs:
+        s.sync()
+        assert s.slab_errors() == 0
+    for name in ("heightmap", "flux", "sediment"):
+        got = np.concatenate([s.download(FIELDS[name]) for s in slabs], axis=0)
+        assert_bit_equal(got, whole.download(FIELDS[name]), f"slabs after refresh_halo: {name}")
+    for s in slabs:
+        s.close()
+    whole.close(); w.close()
+
+
+def test_halo_timeout_is_sticky(built, monkeypatch):
+    """A rank that never arrives: the waiting slab's halo wait times out (HG_HALO_TIMEOUT_S), and from then on the context
+    refuses to step or sync with HG_ERR_STATE instead of silently running on stale ghost rows."""
+    monkeypatch.setenv("HG_HALO_TIMEOUT_S", "0.3")
+    n = 64
+    a = Context(n, n, row0=0, rows=32)
+    b = Context(n, n, row0=32, rows=32)
+    for i, s in enumerate((a, b)):
+        s.connect_local([a, b], i)
+    for s in (a, b):
+        m = s.get_map(); m.seed = SEED; s.set_map(m)
+        s.gen_heightmap()
+    a.dispatch_grid()            # pushes and signals generation 1; the wait for b's signal sits in front of the next step
+    a.dispatch_grid()            # b never steps: this step's wait times out on the device
+    with pytest.raises(_lib.HydrogenError, match="halo wait timed out"):
+        a.sync()
+    with pytest.raises(_lib.HydrogenError, match="halo wait timed out"):
+        a.dispatch_grid()
+    assert a.slab_errors() >= 1
+    a.close(); b.close()
