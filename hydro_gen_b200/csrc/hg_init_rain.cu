@@ -34,6 +34,15 @@ __global__ void __launch_bounds__(256) k_heightmap(SlabDom d, hg_map_settings_da
 struct RainArgs { const float *rock, *dirt, *water, *total; float *o_rock, *o_dirt, *o_water, *o_total; };
 
 __global__ void __launch_bounds__(256) k_rain(SlabDom d, hg_rain_data set, hg_map_settings_data map_set, float time, RainArgs A) {
+    // the permute tables of the table-form simplex noise (hg_noise.cuh): permute(k), k = 0..579, as int and as float
+    __shared__ int perm_i[HG_PERM_N];
+    __shared__ float perm_f[HG_PERM_N];
+    for (int k = threadIdx.y * blockDim.x + threadIdx.x; k < HG_PERM_N; k += blockDim.x * blockDim.y) {
+        const float p = hg_permute((float)k);
+        perm_f[k] = p; perm_i[k] = (int)p;
+    }
+    __syncthreads();
+    const HgPermTab T{perm_i, perm_f};
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int gy = d.row0 - HG_HALO_ROWS + (int)(blockIdx.y * blockDim.y + threadIdx.y);
     if (x >= d.W || gy < 0 || gy >= d.H || gy >= d.row0 + d.rows + HG_HALO_ROWS) return;
@@ -42,7 +51,7 @@ __global__ void __launch_bounds__(256) k_rain(SlabDom d, hg_rain_data set, hg_ma
     // H.a as its last writer left it: (rock + dirt) + water (smoothing.glsl:101, rain.glsl:54,
     // heightmap.glsl:146); read back when the PASSES schedule materialises it
     float total = A.total ? A.total[i] : rock + dirt + water;
-    water += hg_rain_cell(set, map_set, time, x, gy, total);
+    water += hg_rain_cell(set, map_set, time, x, gy, total, &T);
     A.o_rock[i] = rock; A.o_dirt[i] = dirt; A.o_water[i] = water;
     if (A.o_total) A.o_total[i] = rock + dirt + water;
 }

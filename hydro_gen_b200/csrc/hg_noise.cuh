@@ -68,6 +68,71 @@ HG_FN float hg_simplex(float vx, float vy) {
     return 130.0f * (m0 * g0 + m1 * g1 + m2 * g2);
 }
 
+// ---- table form of gln_simplex for the rain kernel --------------------------------------------------------------
+// Every argument of _permute in gln_simplex is an integer-valued float in [0, 579] (lattice coordinates mod 289, plus
+// a permuted value < 289, plus 0 or 1), so the five permutes of an evaluation are lookups in a table of 580 entries
+// that each CTA fills in shared memory with hg_permute itself: the same bits, 2 conversions + 2 integer mod 289 + 5
+// loads instead of 7 x (3 multiply-adds + a 6-instruction mod 289).  The permute chain was 40 % of k_rain's
+// instructions (profiles/r01i_all_kernels.txt: 92 % of issue slots busy).
+constexpr int HG_PERM_N = 580;
+struct HgPermTab { const int* ti; const float* tf; };      // permute(k) as int and as float
+HG_FN int hg_imod289(int v) { int r = v % 289; return r < 0 ? r + 289 : r; }
+HG_FN float hg_simplex_tab(float vx, float vy, const HgPermTab& T) {
+    const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
+    const float Cz = -0.577350269189626f, Cw = 0.024390243902439f;
+    float s = vx * Cy + vy * Cy;
+    float ix = floorf(vx + s), iy = floorf(vy + s);
+    float t = ix * Cx + iy * Cx;
+    float x0x = vx - ix + t, x0y = vy - iy + t;
+    const bool hi = x0x > x0y;
+    float i1x = hi ? 1.0f : 0.0f;
+    float i1y = hi ? 0.0f : 1.0f;
+    float x1x = x0x + Cx, x1y = x0y + Cx, x2x = x0x + Cz, x2y = x0y + Cz;
+    x1x -= i1x;
+    x1y -= i1y;
+    // lattice coordinates beyond +-2^30 (never reached by map coordinates times a noise scale) take the float path
+    if (!(fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f)) return hg_simplex(vx, vy);
+    const int jx = hg_imod289((int)ix), jy = hg_imod289((int)iy);      // == mod289(ix), mod289(iy): exact integers
+    const int in0 = T.ti[jy], in2 = T.ti[jy + 1];
+    float p0 = T.tf[in0 + jx];
+    float p1 = T.tf[(hi ? in0 : in2) + jx + (hi ? 1 : 0)];
+    float p2 = T.tf[in2 + jx + 1];
+    float m0 = hg_max(0.5f - (x0x * x0x + x0y * x0y), 0.0f);
+    float m1 = hg_max(0.5f - (x1x * x1x + x1y * x1y), 0.0f);
+    float m2 = hg_max(0.5f - (x2x * x2x + x2y * x2y), 0.0f);
+    m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
+    m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
+    float q0 = 2.0f * hg_fract(p0 * Cw) - 1.0f;
+    float q1 = 2.0f * hg_fract(p1 * Cw) - 1.0f;
+    float q2 = 2.0f * hg_fract(p2 * Cw) - 1.0f;
+    float h0 = fabsf(q0) - 0.5f, h1 = fabsf(q1) - 0.5f, h2 = fabsf(q2) - 0.5f;
+    float a0 = q0 - floorf(q0 + 0.5f), a1 = q1 - floorf(q1 + 0.5f), a2 = q2 - floorf(q2 + 0.5f);
+    m0 *= 1.79284291400159f - 0.85373472095314f * (a0 * a0 + h0 * h0);
+    m1 *= 1.79284291400159f - 0.85373472095314f * (a1 * a1 + h1 * h1);
+    m2 *= 1.79284291400159f - 0.85373472095314f * (a2 * a2 + h2 * h2);
+    float g0 = a0 * x0x + h0 * x0y;
+    float g1 = a1 * x1x + h1 * x1y;
+    float g2 = a2 * x2x + h2 * x2y;
+    return 130.0f * (m0 * g0 + m1 * g1 + m2 * g2);
+}
+HG_FN float hg_sfbm_tab(float vx, float vy, const HgFbm& o, const HgPermTab& T) {
+    vx += (o.seed * 100.0f);
+    vy += (o.seed * 100.0f);
+    bool ridge = o.turbulence && o.ridge;
+    float result = 0.0f, amplitude = 1.0f, frequency = 1.0f, maximum = amplitude;
+    for (int i = 0; i < 30; i++) {
+        if (i >= o.octaves) break;
+        float n = hg_simplex_tab(vx * frequency * o.scale, vy * frequency * o.scale, T);
+        if (o.turbulence) n = fabsf(n);
+        if (ridge) n = 1.0f - n;
+        result += n * amplitude;
+        frequency *= o.lacunarity;
+        amplitude *= o.persistance;
+        maximum += amplitude;
+    }
+    return result / maximum;
+}
+
 // gln_sfbm; pow(result, 1.0) is the identity      simplex_noise.glsl:419-456
 HG_FN float hg_sfbm(float vx, float vy, const HgFbm& o) {
     vx += (o.seed * 100.0f);
@@ -217,10 +282,10 @@ HG_FN void hg_heightmap_cell(const hg_map_settings_data& cfg, int x, int y, int 
     dirt *= cfg.max_dirt;
 }
 
-// One cell of rain.glsl:32-56.  `total` is H.a as stored; returns the water increment.
-HG_FN float hg_rain_cell(const hg_rain_data& set, const hg_map_settings_data& map_set, float time, int x, int y, float total) {
+// One cell of rain.glsl:32-56.  `total` is H.a as stored; returns the water increment.  T: null, or the permute tables.
+HG_FN float hg_rain_cell(const hg_rain_data& set, const hg_map_settings_data& map_set, float time, int x, int y, float total, const HgPermTab* T = nullptr) {
     HgFbm opts{hg_fract(time * 1.372914227e3f) * 1000.f, 0.5f, 2.0f, set.drops, 8, false, false};
-    float r = hg_max(0.0f, hg_sfbm((float)x, (float)y, opts));
+    float r = hg_max(0.0f, T ? hg_sfbm_tab((float)x, (float)y, opts, *T) : hg_sfbm((float)x, (float)y, opts));
     float incr = set.amount * r;
     float mountain = total - map_set.max_height * set.mountain_thresh;
     if (mountain > 0.0f) {

@@ -106,6 +106,20 @@ void emul_heightmap(const hg_map_settings_data* cfg, int W, int H, float* rock, 
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) hg_heightmap_cell(*cfg, x, y, W, H, rock[(size_t)y * W + x], dirt[(size_t)y * W + x]);
 }
 
+// table form of gln_simplex (hg_simplex_tab, what k_rain runs) against the float form on n points: number of mismatches
+long emul_simplex_tab_mismatches(const float* xs, const float* ys, long n) {
+    static int ti[HG_PERM_N];
+    static float tf[HG_PERM_N];
+    for (int k = 0; k < HG_PERM_N; k++) { tf[k] = hg_permute((float)k); ti[k] = (int)tf[k]; }
+    HgPermTab T{ti, tf};
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        float a = hg_simplex(xs[i], ys[i]), b = hg_simplex_tab(xs[i], ys[i], T);
+        if (memcmp(&a, &b, 4) != 0) bad++;
+    }
+    return bad;
+}
+
 void emul_rain(const hg_rain_data* set, const hg_map_settings_data* map_set, float time, int W, int H,
                const float* rock, const float* dirt, float* water) {
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {

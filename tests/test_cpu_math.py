@@ -228,3 +228,18 @@ def test_two_lane_thermal_marking_matches_oracle_steep(emul):
             for g, x, name in zip(got, planes_of(w), names):
                 assert_bit_equal(g, x, f"two-lane Kalpha={ka}: {name}")
     w.close()
+
+
+def test_table_form_simplex_equals_float_form(emul):
+    """hg_simplex_tab (the rain kernel's gln_simplex with the five permutes as table lookups) returns the same bits as
+    the float form for 2 M random points: map coordinates times the rain's noise scales, negative and large
+    coordinates, and points on lattice lines."""
+    rng = np.random.default_rng(7)
+    n = 2_000_000
+    xs = np.concatenate([rng.uniform(-70000, 70000, n // 2) * rng.choice([0.02, 0.04, 0.32, 2.56], n // 2),
+                         rng.uniform(-300, 300, n // 4), np.round(rng.uniform(-600, 600, n // 4))]).astype(np.float32)
+    ys = np.concatenate([rng.uniform(-70000, 70000, n // 2) * rng.choice([0.02, 0.04, 0.32, 2.56], n // 2),
+                         rng.uniform(-300, 300, n // 4), np.round(rng.uniform(-600, 600, n // 4))]).astype(np.float32)
+    emul.emul_simplex_tab_mismatches.restype = C.c_long
+    bad = emul.emul_simplex_tab_mismatches(xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p), C.c_long(len(xs)))
+    assert bad == 0
