@@ -26,6 +26,7 @@
 #include "hg_internal.cuh"
 #include "hg_fused_body.cuh"
 #include "hg_fused_body2.cuh"
+#include "hg_fused_body3.cuh"
 #include "hg_plan.cuh"
 
 #ifndef HG_FREE_UNROLL
@@ -252,13 +253,14 @@ __device__ __forceinline__ void cta_barrier() {
     asm volatile("barrier.sync 0;" ::: "memory");
 }
 
-template <int NT, int MINB, int RH, int RT, bool DROPS>
+// SWAP: the hydraulic group on the upper half of the CTA's warps (the SM's warp arbiter prefers the higher warp id).
+template <int NT, int MINB, int RH, int RT, bool DROPS, bool SWAP = false>
 __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) float smb[];
     float* const sm = smb + FusedSmem<NT>::RINGS;
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
-    const bool hydro = threadIdx.x < NT;
-    const int tid = hydro ? threadIdx.x : threadIdx.x - NT;
+    const bool hydro = SWAP ? threadIdx.x >= NT : threadIdx.x < NT;
+    const int tid = threadIdx.x < NT ? threadIdx.x : threadIdx.x - NT;
     int strip, gy0, gy1;
     if (K.plan) {           // balanced partition (hg_plan_*): this CTA's strip and rows come from the plan
         const HgPlanItem it = K.plan[blockIdx.x];
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         gy1 = min(gy0 + K.seg, K.row0 + K.rows);
     }
     unsigned long long t_start = 0;
-    if (K.cta_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    if (K.cta_ns && hydro && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
     const int x = x0 + tid;
     const bool xin = x >= 0 && x < K.W;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
 #undef HG_ROW_H
-        if (K.cta_ns && threadIdx.x == 0) {       // the last barrier has passed: both groups are done with their rows
+        if (K.cta_ns && tid == 0) {       // the last barrier has passed: both groups are done with their rows
             unsigned long long t_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
@@ -335,6 +337,218 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------ three warp groups
+// The row period of k_fused_ws is the latency of ONE thermal warp's row (~690 mostly dependent instructions between two
+// CTA barriers), not the issue slots (75 % busy).  Thermal layer 1 reads layer 0's result only through the R1D ring, so
+// the thermal stages split once more: a CTA of 3*NT threads, threads [0, NT) run L, A, B, threads [NT, 2*NT) run C, D
+// (layer 0) and threads [2*NT, 3*NT) run E, F (layer 1); smoothing (G) goes to group SG.  Three CTAs = 36 warps per SM
+// where k_fused_ws holds 24, each with a dependent chain half as long per row.  R0 / R1: registers of a layer-0 /
+// layer-1 thread; RH + R0 + R1 <= 3 * the launch allocation.
+template <int RL, int R> __device__ __forceinline__ void reg_set() {
+    if (R < RL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+    else if (R > RL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int NT, int MINB, int RH, int R0, int R1, bool DROPS, int SG>
+__global__ void __launch_bounds__(3 * NT, MINB) k_fused_ws3(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int RL = 65536 / (3 * NT * MINB) / 8 * 8;      // launch allocation per thread
+    static_assert(RH + R0 + R1 <= 3 * RL && RH % 8 == 0 && R0 % 8 == 0 && R1 % 8 == 0, "register budget of the three warp groups");
+    extern __shared__ __align__(128) float smb[];
+    float* const sm = smb + FusedSmem<NT>::RINGS;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
+    const int group = threadIdx.x / NT;       // warp-uniform
+    const int tid = threadIdx.x - group * NT;
+    int strip, gy0, gy1;
+    if (K.plan) {
+        const HgPlanItem it = K.plan[blockIdx.x];
+        strip = it.strip; gy0 = it.gy0; gy1 = it.gy1;
+    } else {
+        const int segi = blockIdx.x / K.nstrips;
+        strip = blockIdx.x % K.nstrips;
+        gy0 = K.row0 + segi * K.seg;
+        gy1 = min(gy0 + K.seg, K.row0 + K.rows);
+    }
+    unsigned long long t_start = 0;
+    if (K.cta_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
+    const int x = x0 + tid;
+    const bool xin = x >= 0 && x < K.W;
+    const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
+    const HgFusedPlan pl = hg_fused_plan(gy0, gy1, K.H);
+    const unsigned pitch = (unsigned)K.pitch;
+    unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
+    const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
+    constexpr unsigned BOX_BYTES = DROPS ? (unsigned)(HGF_RAW_LD(NT) * 4 * sizeof(float)) : (unsigned)(FusedSmem<NT>::RAW_BOX * sizeof(float));
+    const int bx0 = x0 - 2;
+#define HG_TMA_ROW(dst, bar, row) (DROPS ? tma_load_3d((dst), &tmap, (bar), 0, bx0, (row)) : tma_load_3d((dst), &tmap, (bar), bx0, (row), 0))
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], BOX_BYTES);
+        HG_TMA_ROW(smb, &bars[0], ly0);
+    }
+    __syncthreads();
+    HgCol c;
+    hg_fused_begin(c);
+    int i = pl.i_begin;
+    if (group == 0) {
+        reg_set<RL, RH>();
+#define HG_ROW_H(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        const int rel = i - pl.i_begin;                                                                              \
+        if (tid == 0 && i < pl.i_end) {                                                                              \
+            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
+            HG_TMA_ROW(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &bars[(rel + 1) & 1], ly0 + rel + 1);       \
+        }                                                                                                            \
+        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS, SG>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#undef HG_ROW_H
+        if (K.cta_ns && threadIdx.x == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
+        }
+    } else if (group == 1) {
+        reg_set<RL, R0>();
+#define HG_ROW_T(G, FREEFLAG)                                                                                        \
+    {                                                                                                                \
+        hg_fused_iter<NT, FREEFLAG, G, DROPS, SG>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);              \
+        cta_barrier();                                                                                               \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(HGF_THERMAL0, false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(HGF_THERMAL0, true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(HGF_THERMAL0, false)
+    } else {
+        reg_set<RL, R1>();
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(HGF_THERMAL1, false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(HGF_THERMAL1, true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(HGF_THERMAL1, false)
+#undef HG_ROW_T
+#undef HG_TMA_ROW
+    }
+}
+
+// ------------------------------------------------------------------ queued thermal outflow (hg_fused_body3.cuh)
+// CTA = NT hydraulic threads + NT thermal threads + NSVC service warps.  The thermal threads only test their cell and
+// queue the marked ones; the service warps evaluate thermal_erosion.glsl:59-115 for the queued cells of the whole CTA, 32
+// per pass, one iteration later.  One CTA barrier per row as before.
+template <int NT> struct FusedSmemQ {
+    static constexpr size_t RAW_BOX = (size_t)HGF_NPL * HGF_RAW_LD(NT);
+    static constexpr size_t RAW_SLOT = (RAW_BOX + 31) / 32 * 32;
+    static constexpr size_t RINGS = 2 * RAW_SLOT;
+    static constexpr size_t BARS = (RINGS + HgRingsQ<NT>::TOTAL + 3) / 4 * 4;
+    static constexpr size_t BYTES = (BARS + 4) * sizeof(float);
+};
+
+template <int NT, int MINB, int NSVC, bool DROPS>
+__global__ void __launch_bounds__(2 * NT + 32 * NSVC, MINB) k_fused_q(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) float smb[];
+    float* const sm = smb + FusedSmemQ<NT>::RINGS;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmemQ<NT>::BARS);
+    const int group = threadIdx.x < NT ? HGF_HYDRO : threadIdx.x < 2 * NT ? HGF_THERMAL : HGQ_SERVICE;      // warp-uniform
+    const int tid = group == HGF_HYDRO ? threadIdx.x : group == HGF_THERMAL ? threadIdx.x - NT : threadIdx.x - 2 * NT;
+    int strip, gy0, gy1;
+    if (K.plan) {
+        const HgPlanItem it = K.plan[blockIdx.x];
+        strip = it.strip; gy0 = it.gy0; gy1 = it.gy1;
+    } else {
+        const int segi = blockIdx.x / K.nstrips;
+        strip = blockIdx.x % K.nstrips;
+        gy0 = K.row0 + segi * K.seg;
+        gy1 = min(gy0 + K.seg, K.row0 + K.rows);
+    }
+    unsigned long long t_start = 0;
+    if (K.cta_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    const int x0 = strip * (NT - 2 * HGF_HX) - HGF_HX;
+    const int x = x0 + tid;
+    const bool xin = x >= 0 && x < K.W;
+    const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
+    const HgFusedPlan pl = hg_fusedq_plan(gy0, gy1, K.H);
+    const unsigned pitch = (unsigned)K.pitch;
+    unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
+    const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
+    constexpr unsigned BOX_BYTES = DROPS ? (unsigned)(HGF_RAW_LD(NT) * 4 * sizeof(float)) : (unsigned)(FusedSmemQ<NT>::RAW_BOX * sizeof(float));
+    const int bx0 = x0 - 2;
+#define HG_TMA_ROW(dst, bar, row) (DROPS ? tma_load_3d((dst), &tmap, (bar), 0, bx0, (row)) : tma_load_3d((dst), &tmap, (bar), bx0, (row), 0))
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bars[0], BOX_BYTES);
+        HG_TMA_ROW(smb, &bars[0], ly0);
+    }
+    if (threadIdx.x < 4) reinterpret_cast<unsigned*>(reinterpret_cast<char*>(sm) + HgRingsQ<NT>::QCNT)[threadIdx.x] = 0u;
+    __syncthreads();
+    int i = pl.i_begin;
+    int m3 = (i - 3 + 3 * (1 << 20)) % 3;       // (i - 3) mod 3, i may be negative
+    if (group == HGF_HYDRO) {
+        HgColQ c;
+        hg_colq_init(c);
+#define HG_ROW_H(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        const int rel = i - pl.i_begin;                                                                              \
+        if (tid == 0 && i < pl.i_end) {                                                                              \
+            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
+            HG_TMA_ROW(smb + ((rel + 1) & 1) * FusedSmemQ<NT>::RAW_SLOT, &bars[(rel + 1) & 1], ly0 + rel + 1);      \
+        }                                                                                                            \
+        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        hg_fusedq_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmemQ<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, m3, off); \
+        cta_barrier();                                                                                               \
+        m3 = m3 == 2 ? 0 : m3 + 1;                                                                                   \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
+#undef HG_ROW_H
+        if (K.cta_ns && threadIdx.x == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            K.cta_ns[blockIdx.x] = (unsigned)(t_end - t_start);
+        }
+    } else if (group == HGF_THERMAL) {
+        HgColQ c;
+        hg_colq_init(c);
+#define HG_ROW_T(FREEFLAG)                                                                                           \
+    {                                                                                                                \
+        hg_fusedq_iter<NT, FREEFLAG, HGF_THERMAL, DROPS>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, m3, off);   \
+        cta_barrier();                                                                                               \
+        m3 = m3 == 2 ? 0 : m3 + 1;                                                                                   \
+    }
+        for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#pragma unroll 1
+        for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
+        for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
+#undef HG_ROW_T
+    } else {
+        // service warps: the cells queued during the previous iteration, 32 per pass, alternating between the warps
+        typedef HgRingsQ<NT> R;
+        char* const smc = reinterpret_cast<char*>(sm);
+        volatile unsigned* const qcnt = reinterpret_cast<volatile unsigned*>(smc + R::QCNT);
+        const unsigned short* const qbuf = reinterpret_cast<const unsigned short*>(smc + R::QUEUE);
+#pragma unroll 1
+        for (; i <= pl.i_end; i++) {
+            const unsigned n = qcnt[(i - 1) & 3];
+            for (unsigned b = (unsigned)tid; b < n; b += 32u * NSVC)
+                hg_fusedq_serve<NT>(sm, K, i, m3, qbuf[((i - 1) & 1) * (2 * NT) + b]);
+            if (tid == 0) qcnt[(i + 1) & 3] = 0u;
+            cta_barrier();
+            m3 = m3 == 2 ? 0 : m3 + 1;
+        }
+    }
+#undef HG_TMA_ROW
+}
 
 // ------------------------------------------------------------------ two columns per thread (hg_fused_body2.cuh)
 // Same warp-specialised shell; a CTA of 2*NT threads owns a PAIR of adjacent strips and every thread carries column t
@@ -558,7 +772,7 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     return HG_OK;
 }
 
-template <int NT, int MINB, int RH, int RT, bool DROPS = false>
+template <int NT, int MINB, int RH, int RT, bool DROPS = false, bool SWAP = false>
 static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     static_assert((RH + RT) / 2 * 2 * NT * MINB <= 65536 && RH % 8 == 0 && RT % 8 == 0, "register budget of the two warp groups");
     HgFusedK K = K0;
@@ -568,19 +782,63 @@ static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     constexpr size_t smem = FusedSmem<NT>::BYTES;
     static bool attr_set[HG_MAX_DEVICES] = {};
     if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
-        HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT, DROPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA(cudaFuncSetAttribute(k_fused_ws<NT, MINB, RH, RT, DROPS, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
     }
     alignas(64) CUtensorMap tmap;
     int rc = DROPS ? make_tmap_aos(c, reinterpret_cast<const float4*>(K.ha_src), HGF_RAW_LD(NT), &tmap) : make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
     if (rc) return rc;
     if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
-    k_fused_ws<NT, MINB, RH, RT, DROPS><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
+    k_fused_ws<NT, MINB, RH, RT, DROPS, SWAP><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT, smem, c->stream>>>(K, tmap);
     HG_LAUNCH_CHECK(c);
     if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
     return HG_OK;
 }
 
+
+template <int NT, int MINB, int RH, int R0, int R1, bool DROPS = false, int SG = HGF_THERMAL0>
+static int launch_ws3(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
+    HgFusedK K = K0;
+    K.nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
+    K.seg = seg;
+    int nseg = (c->g.rows + seg - 1) / seg;
+    constexpr size_t smem = FusedSmem<NT>::BYTES;
+    static bool attr_set[HG_MAX_DEVICES] = {};
+    if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
+        HG_CUDA(cudaFuncSetAttribute(k_fused_ws3<NT, MINB, RH, R0, R1, DROPS, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
+    }
+    alignas(64) CUtensorMap tmap;
+    int rc = DROPS ? make_tmap_aos(c, reinterpret_cast<const float4*>(K.ha_src), HGF_RAW_LD(NT), &tmap) : make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
+    if (rc) return rc;
+    if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
+    k_fused_ws3<NT, MINB, RH, R0, R1, DROPS, SG><<<K.plan ? c->plan_n : K.nstrips * nseg, 3 * NT, smem, c->stream>>>(K, tmap);
+    HG_LAUNCH_CHECK(c);
+    if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
+    return HG_OK;
+}
+
+template <int NT, int MINB, int NSVC, bool DROPS = false>
+static int launch_q(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
+    HgFusedK K = K0;
+    K.nstrips = (c->g.W + (NT - 2 * HGF_HX) - 1) / (NT - 2 * HGF_HX);
+    K.seg = seg;
+    int nseg = (c->g.rows + seg - 1) / seg;
+    constexpr size_t smem = FusedSmemQ<NT>::BYTES;
+    static bool attr_set[HG_MAX_DEVICES] = {};
+    if (c->device >= HG_MAX_DEVICES || !attr_set[c->device]) {
+        HG_CUDA(cudaFuncSetAttribute(k_fused_q<NT, MINB, NSVC, DROPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (c->device < HG_MAX_DEVICES) attr_set[c->device] = true;
+    }
+    alignas(64) CUtensorMap tmap;
+    int rc = DROPS ? make_tmap_aos(c, reinterpret_cast<const float4*>(K.ha_src), HGF_RAW_LD(NT), &tmap) : make_tmap(c, src_set, HGF_RAW_LD(NT), &tmap);
+    if (rc) return rc;
+    if (c->prof_ev0) HG_CUDA(cudaEventRecord(c->prof_ev0, c->stream));
+    k_fused_q<NT, MINB, NSVC, DROPS><<<K.plan ? c->plan_n : K.nstrips * nseg, 2 * NT + 32 * NSVC, smem, c->stream>>>(K, tmap);
+    HG_LAUNCH_CHECK(c);
+    if (c->prof_ev1) HG_CUDA(cudaEventRecord(c->prof_ev1, c->stream));
+    return HG_OK;
+}
 
 // two columns per thread: the strips of the launch are strip PAIRS of 2 * (NT - 12) owned columns
 template <int NT, int MINB, int RH, int RT>
@@ -689,13 +947,18 @@ static int launch_fused(hg_ctx* c, bool drops) {
     // CTA shape (threads, resident CTAs per SM); HG_FUSED_VARIANT / HG_FUSED_SEG override (tuning aids)
     // variants 5..: warp-specialised (k_fused_ws), 2 warp groups per CTA
     // variants 10..: two columns per thread (k_fused_ws2): strip pairs, 2 CTAs of 256 threads per SM
-    constexpr int NVAR = 13;
-    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128};
-    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2};
-    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8};
+    // variants 13..: three warp groups per CTA (k_fused_ws3)
+    // variants 18..: queued thermal outflow with service warps (k_fused_q)
+    // variants 21..23: k_fused_ws with the groups swapped / 192-column strips
+    constexpr int NVAR = 24;
+    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 192, 192};
+    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2};
+    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 12, 12, 12, 12, 12, 9, 10, 12, 8, 12, 12};
     int v = c->tune_variant >= 0 && c->tune_variant < NVAR ? c->tune_variant : HG_FUSED_DEFAULT_VARIANT;
-    if (drops) v = c->tune_drops_variant == 1 ? 3 : 5;      // HG_DROPS_VARIANT=1: one warp group of 224 threads runs every stage
-    const bool two_lane = v >= 10;
+    if (drops) v = c->tune_drops_variant == 1 ? 3 : c->tune_drops_variant == 2 ? 13 : c->tune_drops_variant == 3 ? 18 : 5;      // HG_DROPS_VARIANT=1: one warp group of 224 threads runs every stage; 2: three groups
+    const bool two_lane = v >= 10 && v < 13;
+    const bool three_groups = v >= 13;      // (and every later multi-group kernel: they all take the balanced partition)      // (and the queued kernels: every multi-group kernel takes the balanced partition)
+    const bool queued = v >= 18;
     const int NT = nt_of[v];
     const int strip_w = two_lane ? 2 * HGF2_HALF(NT) : NT - 2 * HGF_HX;      // owned columns per CTA
     int nstrips = (c->g.W + strip_w - 1) / strip_w;
@@ -724,7 +987,7 @@ static int launch_fused(hg_ctx* c, bool drops) {
     PlanArgs plan_args{};
     // (droplet slabs keep uniform segments: the first use of a plan allocates and synchronises, which a host thread
     // driving several slabs of one process must not do between two exchange generations)
-    if ((v == 5 || two_lane) && c->tune_seg <= 0 && !c->no_balance && !(drops && c->peers_connected)) {
+    if ((v == 5 || two_lane || three_groups) && c->tune_seg <= 0 && !c->no_balance && !(drops && c->peers_connected)) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // Only with at least six segments per strip: with fewer (16384 columns: 3.1 per strip) one segment more or
@@ -776,7 +1039,18 @@ static int launch_fused(hg_ctx* c, bool drops) {
     case 9: rc = launch_ws<128, 4, 56, 72>(c, K, seg, c->ri[0]); break;
     case 10: rc = launch_ws2<128, 2, 120, 136>(c, K, seg, c->ri[0]); break;
     case 11: rc = launch_ws2<128, 2, 128, 128>(c, K, seg, c->ri[0]); break;
-    default: rc = launch_ws2<128, 2, 112, 144>(c, K, seg, c->ri[0]); break;
+    case 12: rc = launch_ws2<128, 2, 112, 144>(c, K, seg, c->ri[0]); break;
+    case 13: rc = drops ? launch_ws3<128, 3, 56, 56, 56, true>(c, K, seg, c->ri[0]) : launch_ws3<128, 3, 72, 48, 48, false, HGF_THERMAL0>(c, K, seg, c->ri[0]); break;
+    case 14: rc = launch_ws3<128, 3, 64, 48, 56, false, HGF_THERMAL1>(c, K, seg, c->ri[0]); break;
+    case 15: rc = launch_ws3<128, 3, 64, 56, 48, false, HGF_THERMAL0>(c, K, seg, c->ri[0]); break;
+    case 16: rc = launch_ws3<128, 3, 72, 48, 48, false, HGF_THERMAL1>(c, K, seg, c->ri[0]); break;
+    case 17: rc = launch_ws3<128, 3, 64, 48, 56, false, HGF_THERMAL0>(c, K, seg, c->ri[0]); break;
+    case 18: rc = drops ? launch_q<128, 3, 1, true>(c, K, seg, c->ri[0]) : launch_q<128, 3, 1>(c, K, seg, c->ri[0]); break;
+    case 19: rc = launch_q<128, 3, 2>(c, K, seg, c->ri[0]); break;
+    case 20: rc = launch_q<128, 3, 4>(c, K, seg, c->ri[0]); break;
+    case 21: rc = launch_ws<128, 3, 72, 88, false, true>(c, K, seg, c->ri[0]); break;
+    case 22: rc = launch_ws<192, 2, 80, 80>(c, K, seg, c->ri[0]); break;      // (setmaxnreg works on whole warpgroups of 4 warps: a 6 + 6 warp CTA cannot rebalance)
+    default: rc = launch_ws<192, 2, 80, 80, false, true>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     if (balanced) {

@@ -59,7 +59,10 @@
 #define HGF_ATOMIC_INC64(p) ((*(p))++)
 #endif
 
-constexpr int HGF_ALL = 0, HGF_HYDRO = 1, HGF_THERMAL = 2;   // which stages a warp group runs
+// which stages a warp group runs: everything / L, A, B / C..G / C, D (thermal layer 0) / E, F (thermal layer 1).
+// Layer 1 reads layer 0's result only through the R1D ring, so the thermal stages split between two groups the same
+// way the hydraulic and thermal stages do (k_fused_ws3: three warp groups per CTA).
+constexpr int HGF_ALL = 0, HGF_HYDRO = 1, HGF_THERMAL = 2, HGF_THERMAL0 = 3, HGF_THERMAL1 = 4;
 #ifndef HGF_SMOOTH_GROUP
 #define HGF_SMOOTH_GROUP HGF_THERMAL
 #endif
@@ -147,7 +150,7 @@ HG_FN void hg_col_init(HgCol& c) {
 // thread; xin/owned: column inside the map / inside the strip proper; gy0, gy1: the CTA's
 // row segment; off: element offset of (row i, column x) inside a plane.
 // FREE: see the header.
-template <int NT, bool FREE, int GROUP = HGF_ALL, bool DROPS = false>
+template <int NT, bool FREE, int GROUP = HGF_ALL, bool DROPS = false, int SG = HGF_SMOOTH_GROUP>
 HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& K, const int tid, const int x, const bool xin, const bool owned,
                          const int gy0, const int gy1, const int i, const unsigned off) {
     typedef HgRings<NT> R;
@@ -155,6 +158,9 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     const int W = K.W, H = K.H;
     const unsigned pitch = (unsigned)K.pitch;
     const int e = tid + 1;   // element index inside a ring row
+    constexpr bool RUN_H = GROUP == HGF_ALL || GROUP == HGF_HYDRO;
+    constexpr bool RUN_CD = GROUP == HGF_ALL || GROUP == HGF_THERMAL || GROUP == HGF_THERMAL0;
+    constexpr bool RUN_EF = GROUP == HGF_ALL || GROUP == HGF_THERMAL || GROUP == HGF_THERMAL1;
     char* const smc = reinterpret_cast<char*>(sm);
     // Element index (slot * E + e) of the ring row that holds absolute row i - j: two-row rings
     // (j = 0, 1) and four-row rings (j = 0..3).  Row i - k lives in slot (i - k) mod n.
@@ -172,7 +178,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
 #define Q2(ring, k, d) (*reinterpret_cast<HgF2*>(B8(k) + (ring) + (d) * 8))
 #define Q2X(ring, k, d) (reinterpret_cast<const float*>(B8(k) + (ring) + (d) * 8)[0])   /* .x only: a 4-byte load */
 
-    if (GROUP != HGF_THERMAL && DROPS) {
+    if (RUN_H && DROPS) {
     // ------------------------------------------------------------ droplet mode: no hydraulics
     // Erosion::dispatch_particle (src/erosion.cpp:146-155) runs thermal x2 + smoothing on the heightmap the droplets
     // left: this group only feeds the thermal group with (rock, dirt) of row i-1, as stage A does with (rockE, dirtE).
@@ -191,7 +197,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         }
     }
     }
-    if (GROUP != HGF_THERMAL && !DROPS) {
+    if (RUN_H && !DROPS) {
     // ------------------------------------------------------------ L(i)
     c.rk0 = c.rk1; c.rk1 = c.rk2; c.dt0 = c.dt1; c.dt1 = c.dt2; c.at0 = c.at1; c.at1 = c.at2; c.w1 = c.w2;
     c.f0T = c.f1T; c.f1L = c.f2L; c.f1R = c.f2R; c.f1T = c.f2T; c.f1B = c.f2B; c.s1r = c.s2r; c.s1d = c.s2d;
@@ -224,8 +230,12 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             // FREE rows are strictly inside the map in y: y = 1, H = 4 folds the y-border tests away
             HgFluxOut o = hg_flux_cell(P, x, FREE ? 1 : ya, W, FREE ? 4 : H, c.at1, ql.x, qr.x, c.at2, c.at0,
                                        c.f1L, c.f1R, c.f1T, c.f1B, ql.w, inR, c.f2B, c.f0T, c.w1);
+#ifdef HG_EXP_NO_ERO
+            HgEroOut er; er.rock = c.rk1 + qr.y * 0.001f; er.dirt = c.dt1 + ql.z * 0.001f; er.sr = c.s1r + o.u * 0.001f; er.sd = c.s1d + o.vz * 0.001f;
+#else
             HgEroOut er = hg_erosion_cell(P, c.rk1, c.dt1, c.s1r, c.s1d, o.u, o.v, o.vz,
                                           qr.y, qr.z, ql.y, ql.z, c.rk0, c.dt0, c.rk2, c.dt2);
+#endif
             u_new = o.u; v_new = o.v;
             if (owned && in && (FREE || (ya >= gy0 && ya < gy1))) {
                 const unsigned idx = off - pitch;
@@ -243,6 +253,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     // ------------------------------------------------------------ B(i-3)
     {
         const int yb = i - 3;
+#ifndef HG_EXP_NO_B
         if (FREE || (yb >= gy0 && yb < gy1)) {
             HgBack b = hg_backtrace(P, x, yb, W, H, c.u_d2, c.v_d2);
             const int dx = b.px - x, dy = b.py - yb;
@@ -266,14 +277,14 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 }
             }
         }
+#endif
     }
 
     c.u_d2 = c.u_d1; c.v_d2 = c.v_d1; c.u_d1 = u_new; c.v_d1 = v_new;
-    }   // GROUP != HGF_THERMAL
+    }   // RUN_H
 
-    if (GROUP != HGF_HYDRO) {
     // ------------------------------------------------------------ C(i-3), D(i-5)
-    {
+    if (RUN_CD) {
         // rockE window: rows i-4 (y-1), i-3 (y), i-2 (y+1), columns x-1..x+1, straight from the ring
         // (stage A writes row i-1 into the fourth slot meanwhile)
         const HgF2 rd01 = Q2(R::RD, 4, 0);
@@ -316,7 +327,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     }
 
     // ------------------------------------------------------------ E(i-7), F(i-9)
-    {
+    if (RUN_EF) {
         // (rock1, dirtE) window: rows i-8 (y-1), i-7 (y), i-6 (y+1), columns x-1..x+1, from the ring
         // (stage D writes row i-5 into the fourth slot meanwhile)
         const HgF2 w00 = Q2(R::R1D, 8, -1), w01 = Q2(R::R1D, 8, 0), w02 = Q2(R::R1D, 8, 1);
@@ -356,8 +367,6 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         c.nRT1_d2 = c.nRT1_d1; c.nRT1_d1 = nl.y; c.nLT1_d2 = c.nLT1_d1; c.nLT1_d1 = nr.y;
     }
 
-    }   // GROUP != HGF_HYDRO
-
     // ------------------------------------------------------------ G(i-11)
     // (Layer 1 on the hydraulic group in droplet mode -- it reads layer 0's result only through the R1D ring -- evens the
     // instruction counts of the two groups, 520 / 310 per row instead of 206 / 599, and was measured 5 % SLOWER:
@@ -367,7 +376,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
     // slower (its instruction stream is the latency-heavy one: divisions, sqrt, the TMA wait).
     // Droplet mode: the hydraulic group only feeds rows to the thermal group, so it takes the smoothing stage
     // (and the momentum map) off the thermal group's hands.
-    if (GROUP == HGF_ALL || GROUP == (DROPS ? HGF_HYDRO : HGF_SMOOTH_GROUP)) {
+    if (GROUP == HGF_ALL || GROUP == (DROPS ? HGF_HYDRO : SG)) {
         // own column of (rock1, dirt2): rows i-12 (y-1), i-11 (y), i-10 (y+1); stage F writes row i-9 meanwhile
         const int yg = i - HGF_LAG_G;
         if (FREE || (yg >= gy0 && yg < gy1)) {

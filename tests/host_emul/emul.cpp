@@ -10,6 +10,7 @@
 #include "../../hydro_gen_b200/csrc/hg_noise.cuh"
 #include "../../hydro_gen_b200/csrc/hg_fused_body.cuh"
 #include "../../hydro_gen_b200/csrc/hg_fused_body2.cuh"
+#include "../../hydro_gen_b200/csrc/hg_fused_body3.cuh"
 
 namespace {
 struct Dom { int W, H; };
@@ -272,6 +273,85 @@ static long fused2_step_emul(const hg_erosion_data* set, int W, int H, int seg, 
 extern "C" long emul_fused2_step(const hg_erosion_data* set, int W, int H, int nt, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
     if (nt == 32) return fused2_step_emul<32>(set, W, H, seg, ws, src, dst, far_out);
     if (nt == 128) return fused2_step_emul<128>(set, W, H, seg, ws, src, dst, far_out);
+    return -1;
+}
+
+// The queued-outflow body (hg_fused_body3.cuh, k_fused_q) run the same way: hydraulic threads, thermal threads and the
+// service role (the cells queued during the previous iteration) within an iteration in the order `ws` names --
+// 1: H T S, 2: S T H, 3: T S H, 4: S H T -- all of which the GPU may produce between two barriers.  The queue starts each
+// CTA empty, smem starts as garbage-free zeros here (the kernel never reads an element it did not write for a cell
+// whose result is used).
+template <int NT>
+static long fusedq_step_emul(const hg_erosion_data* set, int W, int H, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    const int HALO = 8;
+    typedef HgRingsQ<NT> R;
+    size_t pe = (size_t)(H + 2 * HALO) * W;
+    std::vector<std::vector<float>> ps(9, std::vector<float>(pe, 0.0f)), pd(9, std::vector<float>(pe, 0.0f));
+    for (int p = 0; p < 9; p++) memcpy(ps[p].data() + (size_t)HALO * W, src[p], (size_t)W * H * 4);
+    unsigned long long far_count = 0;
+    HgFusedK K;
+    memset(&K, 0, sizeof(K));
+    for (int p = 0; p < 9; p++) { K.src[p] = ps[p].data(); K.dst[p] = pd[p].data(); }
+    K.W = W; K.H = H; K.row0 = 0; K.rows = H; K.pitch = W; K.seg = seg;
+    K.nstrips = (W + (NT - 12) - 1) / (NT - 12);
+    K.far_list = far_out; K.far_count = &far_count;
+    K.P = hg_make_step_params(*set);
+    int nseg = (H + seg - 1) / seg;
+    std::vector<float> sm(R::TOTAL + 4);
+    std::vector<HgColQ> cols(NT), colsT(NT);
+    for (int blk = 0; blk < K.nstrips * nseg; blk++) {
+        // poison instead of zeros: a value read before it was written for a cell that matters shows up as a mismatch
+        for (auto& f : sm) f = 12345.678f;
+        float* smp = sm.data();
+        while ((uintptr_t)smp % 16) smp++;
+        unsigned* qcnt = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(smp) + R::QCNT);
+        const unsigned short* qbuf = reinterpret_cast<const unsigned short*>(reinterpret_cast<char*>(smp) + R::QUEUE);
+        for (int k = 0; k < 4; k++) qcnt[k] = 0u;
+        int strip = blk % K.nstrips, segi = blk / K.nstrips;
+        int gy0 = segi * seg, gy1 = gy0 + seg < H ? gy0 + seg : H;
+        HgFusedPlan pl = hg_fusedq_plan(gy0, gy1, H);
+        auto xof = [&](int tid) { return strip * (NT - 12) - 6 + tid; };
+        for (int tid = 0; tid < NT; tid++) { hg_colq_init(cols[tid]); hg_colq_init(colsT[tid]); }
+        std::vector<float> raw(9 * HGF_RAW_LD(NT));
+        for (int i = pl.i_begin; i <= pl.i_end; i++) {
+            bool fr = i >= pl.free_lo && i <= pl.free_hi;
+            const int m3 = ((i - 3) % 3 + 3) % 3;
+            for (int p = 0; p < 9; p++) for (int t = 0; t < HGF_RAW_LD(NT); t++) {
+                int x = xof(0) - 2 + t, lr = i + HALO;
+                raw[p * HGF_RAW_LD(NT) + t] = (x >= 0 && x < W && lr >= 0 && lr < H + 2 * HALO) ? ps[p][(size_t)lr * W + x] : 0.0f;
+            }
+            auto run_group = [&](int group) {
+                if (group == HGQ_SERVICE) {
+                    const unsigned n = qcnt[(i - 1) & 3];
+                    for (unsigned b = 0; b < n; b++) hg_fusedq_serve<NT>(smp, K, i, m3, qbuf[((i - 1) & 1) * (2 * NT) + b]);
+                    qcnt[(i + 1) & 3] = 0u;
+                    return;
+                }
+                for (int tid = 0; tid < NT; tid++) {
+                    int x = xof(tid);
+                    bool xin = x >= 0 && x < W, owned = tid >= 6 && tid < NT - 6 && x < W;
+                    unsigned off = (unsigned)(i + HALO) * (unsigned)W + (unsigned)x;
+                    if (group == HGF_HYDRO) {
+                        if (fr) hg_fusedq_iter<NT, true, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, m3, off);
+                        else hg_fusedq_iter<NT, false, HGF_HYDRO>(cols[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, m3, off);
+                    } else {
+                        if (fr) hg_fusedq_iter<NT, true, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, m3, off);
+                        else hg_fusedq_iter<NT, false, HGF_THERMAL>(colsT[tid], smp, raw.data(), K, tid, x, xin, owned, gy0, gy1, i, m3, off);
+                    }
+                }
+            };
+            static const int order[5][3] = {{HGF_HYDRO, HGF_THERMAL, HGQ_SERVICE}, {HGF_HYDRO, HGF_THERMAL, HGQ_SERVICE}, {HGQ_SERVICE, HGF_THERMAL, HGF_HYDRO},
+                                            {HGF_THERMAL, HGQ_SERVICE, HGF_HYDRO}, {HGQ_SERVICE, HGF_HYDRO, HGF_THERMAL}};
+            for (int g = 0; g < 3; g++) run_group(order[ws >= 0 && ws < 5 ? ws : 0][g]);
+        }
+    }
+    for (int p = 0; p < 9; p++) memcpy(dst[p], pd[p].data() + (size_t)HALO * W, (size_t)W * H * 4);
+    return (long)far_count;
+}
+
+extern "C" long emul_fusedq_step(const hg_erosion_data* set, int W, int H, int nt, int seg, int ws, const float* const src[9], float* const dst[9], unsigned* far_out) {
+    if (nt == 32) return fusedq_step_emul<32>(set, W, H, seg, ws, src, dst, far_out);
+    if (nt == 128) return fusedq_step_emul<128>(set, W, H, seg, ws, src, dst, far_out);
     return -1;
 }
 

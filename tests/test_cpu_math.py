@@ -139,7 +139,7 @@ def test_struct_layouts_match_the_reference():
     assert oracle.PARTICLE_DTYPE.fields["sediment"][1] == 32 and oracle.PARTICLE_DTYPE.fields["to_kill"][1] == 40
 
 
-def fused_emul_step(E, w, nt, seg, ws=0, two_lane=False):
+def fused_emul_step(E, w, nt, seg, ws=0, two_lane=False, queued=False):
     """one step of the fused kernel body on the CPU; returns (planes, far cell indices)"""
     src = planes_of(w)
     dst = [np.zeros_like(p) for p in src]
@@ -147,7 +147,7 @@ def fused_emul_step(E, w, nt, seg, ws=0, two_lane=False):
     sa = (C.c_void_p * 9)(*[p.ctypes.data for p in src])
     da = (C.c_void_p * 9)(*[p.ctypes.data for p in dst])
     er = hl.ErosionData.from_buffer_copy(bytes(w.erosion))
-    fn = E.emul_fused2_step if two_lane else E.emul_fused_step
+    fn = E.emul_fusedq_step if queued else E.emul_fused2_step if two_lane else E.emul_fused_step
     fn.restype = C.c_long
     n = fn(C.byref(er), w.W, w.H, nt, seg, ws, sa, da, far.ctypes.data_as(C.c_void_p))
     assert n >= 0
@@ -178,6 +178,31 @@ def test_fused_kernel_body_emulated_matches_oracle(emul, nt, seg, shape, ws):
                 g = np.where(mask.reshape(H, W), g, x)
             assert_bit_equal(g, x, f"nt={nt} seg={seg} {name}")
         total_far += len(far)
+    w.close()
+
+
+@pytest.mark.parametrize("nt,seg,shape,ws", [(32, 16, (72, 64), 1), (32, 64, (40, 136), 2), (32, 16, (72, 64), 3), (128, 32, (192, 96), 4),
+                                             (128, 128, (128, 160), 2), (128, 48, (240, 64), 1)])
+def test_queued_outflow_body_emulated_matches_oracle(emul, nt, seg, shape, ws):
+    """hg_fused_body3.cuh -- the code k_fused_q runs: thermal threads only test their cell and queue the marked ones, a
+    service role evaluates the outflow of the queued cells one iteration later -- executed thread by thread on the CPU
+    with the three roles of an iteration in four different orders, against the oracle: every plane bit-exact.  The
+    rings start poisoned, so a value consumed before it was produced would show."""
+    W, H = shape
+    w = wet_world(H, 120, width=W, period=8)
+    names = "rock dirt water fL fR fT fB sed_r sed_d".split()
+    for _ in range(3):
+        got, far = fused_emul_step(emul, w, nt, seg, ws, queued=True)
+        pl = planes_of(w)
+        far_ref = emul_step(emul, w, pl)
+        w.step((w.steps + 1) * DT_TIME)
+        want = planes_of(w)
+        assert len(far) == far_ref
+        mask = np.ones(W * H, bool); mask[far] = False
+        for k, (g, x, name) in enumerate(zip(got, want, names)):
+            if k >= 7:
+                g = np.where(mask.reshape(H, W), g, x)
+            assert_bit_equal(g, x, f"queued nt={nt} seg={seg} ws={ws} {name}")
     w.close()
 
 
