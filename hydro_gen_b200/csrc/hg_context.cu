@@ -153,6 +153,7 @@ extern "C" hg_ctx* hg_create_slab(uint32_t map_w, uint32_t map_h, uint32_t row0,
     c->tune_variant = -1;
     if (const char* e = getenv("HG_FUSED_SEG")) c->tune_seg = atoi(e);   // tuning aids
     if (const char* e = getenv("HG_FUSED_VARIANT")) c->tune_variant = atoi(e);
+    if (const char* e = getenv("HG_FUSED_PUSH")) c->no_fused_push = atoi(e) == 0;
     if (const char* e = getenv("HG_FUSED_BALANCE")) c->no_balance = atoi(e) == 0;
     if (const char* e = getenv("HG_DROPS_VARIANT")) c->tune_drops_variant = atoi(e);
     c->p_rebin_period = 8;

@@ -51,6 +51,13 @@ struct FusedArgs {
     unsigned long long* far_count;       // this step's counter
     unsigned long long* far_count_next;  // zeroed by the fix-up kernel for the next step
     unsigned long long* far_total;       // statistics
+    // connected slab with the push fused into the step (HgFusedK::peer): the fix-up repeats its stores of edge-row cells
+    // into the neighbours' ghost rows, and its LAST block publishes the exchange generation on every rank (hg_slab.cu)
+    float* peer[2][2];                   // [side][sediment rock, dirt], pre-offset like HgFusedK::peer
+    int push_mask, push_lo_end, push_hi_begin;
+    HgFlagArgs sig;                      // my flag word on every other rank; n == 0: no signal from this kernel
+    unsigned gen;
+    unsigned* done;                      // block counter (self-resetting)
     HgStepParams P;
 };
 
@@ -133,8 +140,27 @@ __global__ void __launch_bounds__(128) k_far_fixup(const __grid_constant__ Fused
         const float t01d = __shfl_sync(0xffffffffu, td, base + 2), t11d = __shfl_sync(0xffffffffu, td, base + 3);
         if (live && q == 0) {
             size_t idx = (size_t)(ly + HG_HALO_ROWS) * A.pitch + x;
-            A.dst[PL_SR][idx] = hg_bilerp(t00r, t10r, t01r, t11r, b.sx, b.sy);
-            A.dst[PL_SD][idx] = hg_bilerp(t00d, t10d, t01d, t11d, b.sx, b.sy);
+            const float vr = hg_bilerp(t00r, t10r, t01r, t11r, b.sx, b.sy), vd = hg_bilerp(t00d, t10d, t01d, t11d, b.sx, b.sy);
+            A.dst[PL_SR][idx] = vr;
+            A.dst[PL_SD][idx] = vd;
+            if ((A.push_mask & 1) && gy < A.push_lo_end) { A.peer[0][0][idx] = vr; A.peer[0][1][idx] = vd; }
+            if ((A.push_mask & 2) && gy >= A.push_hi_begin) { A.peer[1][0][idx] = vr; A.peer[1][1][idx] = vd; }
+        }
+    }
+    if (A.sig.n) {
+        // Every store of this step into a neighbour's ghost rows -- the step kernel's (complete: it ran before this kernel
+        // on the same stream) and this kernel's -- is ordered before the flag words by the fence + counter + fence of
+        // the last block, as in k_halo_push_signal.
+        __threadfence_system();
+        __syncthreads();
+        __shared__ unsigned last;
+        if (threadIdx.x == 0) last = (atomicAdd(A.done, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) *A.done = 0u;
+            __threadfence_system();
+            if ((int)threadIdx.x < A.sig.n && A.sig.flag[threadIdx.x]) *reinterpret_cast<volatile unsigned*>(A.sig.flag[threadIdx.x]) = A.gen;
+            __threadfence_system();
         }
     }
 }
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     const int x = x0 + tid;
     const bool xin = x >= 0 && x < K.W;
     const bool owned = tid >= HGF_HX && tid < NT - HGF_HX && x < K.W;
-    const HgFusedPlan pl = hg_fused_plan(gy0, gy1, K.H);
+    const HgFusedPlan pl = hg_fused_plan_slab(gy0, gy1, K.H, K);
     const unsigned pitch = (unsigned)K.pitch;
     unsigned off = (unsigned)(pl.i_begin - K.row0 + HG_HALO_ROWS) * pitch + (unsigned)x;
     const int ly0 = pl.i_begin - K.row0 + HG_HALO_ROWS;
@@ -937,6 +963,28 @@ static int launch_fused(hg_ctx* c, bool drops) {
     A.far_total = c->d_counters;
     c->far_parity ^= 1;
     A.P = K.P = c->sp;
+    // Connected grid slab on the default kernel: the step kernel and the fix-up store the edge rows straight into the
+    // neighbours' ghost rows and the fix-up's last block signals the generation -- no separate push kernel
+    // (hg_slab_exchange then only books the generation).  HG_FUSED_PUSH=0: the separate k_halo_push_signal.
+    bool fused_push = false;
+    if (!drops && c->peers_connected && !c->no_fused_push && (c->tune_variant < 0 || c->tune_variant == 5) && HG_FUSED_DEFAULT_VARIANT == 5) {
+        float* pp[2][HG_NPLANES];
+        int mask = 0;
+        int rcp = hg_slab_peer_planes(c, pp, &mask);
+        if (rcp) return rcp;
+        for (int sd = 0; sd < 2; sd++) {
+            for (int p = 0; p < HG_NPLANES; p++) K.peer[sd][p] = pp[sd][p];
+            A.peer[sd][0] = pp[sd][PL_SR]; A.peer[sd][1] = pp[sd][PL_SD];
+        }
+        A.push_mask = K.push_mask = mask;
+        A.push_lo_end = K.push_lo_end = c->g.row0 + HG_HALO_ROWS;
+        A.push_hi_begin = K.push_hi_begin = c->g.row0 + c->g.rows - HG_HALO_ROWS;
+        c->step_flag++;
+        A.gen = c->step_flag;
+        hg_slab_signal_args(c, &A.sig);
+        A.done = reinterpret_cast<unsigned*>(c->d_counters + 11);
+        fused_push = true;
+    }
     if (drops) {
         // heightmap and momentum map in texture layout (hg_particle_layout): read images -> write images
         int rcl = hg_particle_layout(c, true);
@@ -950,10 +998,10 @@ static int launch_fused(hg_ctx* c, bool drops) {
     // variants 13..: three warp groups per CTA (k_fused_ws3)
     // variants 18..: queued thermal outflow with service warps (k_fused_q)
     // variants 21..23: k_fused_ws with the groups swapped / 192-column strips
-    constexpr int NVAR = 24;
-    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 192, 192};
-    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2};
-    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 12, 12, 12, 12, 12, 9, 10, 12, 8, 12, 12};
+    constexpr int NVAR = 25;
+    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 192, 192, 192};
+    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2};
+    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 12, 12, 12, 12, 12, 9, 10, 12, 8, 12, 12, 13};
     int v = c->tune_variant >= 0 && c->tune_variant < NVAR ? c->tune_variant : HG_FUSED_DEFAULT_VARIANT;
     if (drops) v = c->tune_drops_variant == 1 ? 3 : c->tune_drops_variant == 2 ? 13 : c->tune_drops_variant == 3 ? 18 : 5;      // HG_DROPS_VARIANT=1: one warp group of 224 threads runs every stage; 2: three groups
     const bool two_lane = v >= 10 && v < 13;
@@ -1050,7 +1098,8 @@ static int launch_fused(hg_ctx* c, bool drops) {
     case 20: rc = launch_q<128, 3, 4>(c, K, seg, c->ri[0]); break;
     case 21: rc = launch_ws<128, 3, 72, 88, false, true>(c, K, seg, c->ri[0]); break;
     case 22: rc = launch_ws<192, 2, 80, 80>(c, K, seg, c->ri[0]); break;      // (setmaxnreg works on whole warpgroups of 4 warps: a 6 + 6 warp CTA cannot rebalance)
-    default: rc = launch_ws<192, 2, 80, 80, false, true>(c, K, seg, c->ri[0]); break;
+    case 23: rc = launch_ws<192, 2, 80, 80, false, true>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_q<192, 2, 1>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     if (balanced) {
@@ -1075,6 +1124,7 @@ static int launch_fused(hg_ctx* c, bool drops) {
     }
     k_far_fixup<<<148 * 2, 128, 0, c->stream>>>(A);
     HG_LAUNCH_CHECK(c);
+    if (fused_push) c->fused_push_gen = A.gen;      // hg_slab_exchange: already pushed and signalled
     for (int f = 0; f < 4; f++) if (f != 2) c->ri[f] ^= 1;   // H, F, S flip once per fused step; V is not stored
     return HG_OK;
 }

@@ -120,8 +120,22 @@ struct HgFusedK {
     HgF4* ha_dst;
     const HgF4* ma_src;
     HgF4* ma_dst;
+    // row slabs on several GPUs (hg_slab.cu): the rows a neighbour keeps as ghost rows are stored a second time, straight
+    // into that neighbour's planes through its peer pointer (NVLink), by the thread that produces them -- the step kernel
+    // IS the halo push.  push_mask bit 0: rows < push_lo_end also go to peer[0] (the slab below), bit 1: rows >=
+    // push_hi_begin to peer[1] (the slab above); the pointers are pre-offset so that this slab's element index applies.
+    float* peer[2][HGF_NPL];
+    int push_mask, push_lo_end, push_hi_begin;
     HgStepParams P;
 };
+
+// second store of a result row into the neighbours' ghost rows (generic iterations only: the FREE range of a connected
+// slab keeps clear of the edge rows, hg_fused_plan_slab)
+#define HGF_PEER_STORE(K, p, row, idx, val)                                                                  \
+    {                                                                                                        \
+        if (((K).push_mask & 1) && (row) < (K).push_lo_end) (K).peer[0][p][idx] = (val);                     \
+        if (((K).push_mask & 2) && (row) >= (K).push_hi_begin) (K).peer[1][p][idx] = (val);                  \
+    }
 
 // per-thread rolling state (one column)
 struct HgCol {
@@ -242,6 +256,11 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 K.dst[3][idx] = o.fL; K.dst[4][idx] = o.fR;
                 K.dst[5][idx] = o.fT; K.dst[6][idx] = o.fB;
                 K.dst[2][idx] = o.water * P.evap;     // sediment_transport.glsl:75
+                if (!FREE && K.push_mask) {
+                    HGF_PEER_STORE(K, 3, ya, idx, o.fL) HGF_PEER_STORE(K, 4, ya, idx, o.fR)
+                    HGF_PEER_STORE(K, 5, ya, idx, o.fT) HGF_PEER_STORE(K, 6, ya, idx, o.fB)
+                    HGF_PEER_STORE(K, 2, ya, idx, o.water * P.evap)
+                }
             }
             HgF2 rd; rd.x = in ? er.rock : HG_OOB_HEIGHT; rd.y = in ? er.dirt : HG_OOB_HEIGHT;
             Q2(R::RD, 1, 0) = rd;
@@ -271,6 +290,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 if (fast) {
                     K.dst[7][idx] = sr;
                     K.dst[8][idx] = sd;
+                    if (!FREE && K.push_mask) { HGF_PEER_STORE(K, 7, yb, idx, sr) HGF_PEER_STORE(K, 8, yb, idx, sd) }
                 } else {
                     unsigned long long slot = HGF_ATOMIC_INC64(K.far_count);
                     K.far_list[slot] = (unsigned)(yb - K.row0) * (unsigned)W + (unsigned)x;
@@ -403,6 +423,7 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
                 } else {
                     K.dst[0][idx] = border ? rock : sr_;
                     K.dst[1][idx] = border ? dirt : sd_;
+                    if (!FREE && K.push_mask) { HGF_PEER_STORE(K, 0, yg, idx, border ? rock : sr_) HGF_PEER_STORE(K, 1, yg, idx, border ? dirt : sd_) }
                 }
             }
         }
@@ -444,6 +465,18 @@ HG_FN HgFusedPlan hg_fused_plan(int gy0, int gy1, int H) {
     p.i_end = gy1 + HGF_LAG_G - 1;
     hg_fused_free_range(gy0, gy1, H, &p.free_lo, &p.free_hi);
     if (p.free_hi < p.free_lo) { p.free_lo = p.i_end + 1; p.free_hi = p.i_end; }
+    return p;
+}
+
+// Connected slab: FREE iterations carry no peer stores, so they keep clear of the rows the neighbours hold as ghost rows
+// (iteration i produces rows i-11 .. i-1).
+HG_FN HgFusedPlan hg_fused_plan_slab(int gy0, int gy1, int H, const HgFusedK& K) {
+    HgFusedPlan p = hg_fused_plan(gy0, gy1, H);
+    if (K.push_mask) {
+        if ((K.push_mask & 1) && p.free_lo < K.push_lo_end + HGF_LAG_G) p.free_lo = K.push_lo_end + HGF_LAG_G;
+        if ((K.push_mask & 2) && p.free_hi > K.push_hi_begin) p.free_hi = K.push_hi_begin;
+        if (p.free_hi < p.free_lo) { p.free_lo = p.i_end + 1; p.free_hi = p.i_end; }
+    }
     return p;
 }
 

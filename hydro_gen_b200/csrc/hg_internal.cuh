@@ -135,7 +135,12 @@ struct hg_ctx {
     unsigned* d_sticky;
     unsigned long long halo_timeout_ns;
     uint32_t pending_gen;      // generation signalled but not yet waited for (hg_slab_wait_pending), 0 = none
+    uint32_t fused_push_gen;   // generation the last fused step pushed and signalled from inside its own kernels (hg_fused.cu), 0 = none
+    bool no_fused_push;        // HG_FUSED_PUSH=0: keep the separate push kernel (A/B measurements)
 };
+
+// my flag word on every other rank (null for myself)
+struct HgFlagArgs { unsigned* flag[HG_MAX_SLABS]; int n; };
 
 void hg_set_error(const char* fmt, ...);
 
@@ -206,6 +211,10 @@ int hg_preload_particle_kernels(void);
 int hg_preload_init_rain_kernels(void);
 int hg_preload_context_kernels(void);
 int hg_slab_exchange(hg_ctx* c);     // push edge rows to neighbours + wait (no-op without peers)
+// fused push (hg_fused.cu): the neighbours' planes of the set this step WRITES, pre-offset so that this slab's element
+// index (ghost rows included) of an edge row addresses the matching ghost row; mask bit 0 / 1: a slab below / above exists
+int hg_slab_peer_planes(const hg_ctx* c, float* out[2][HG_NPLANES], int* mask);
+void hg_slab_signal_args(const hg_ctx* c, HgFlagArgs* out);
 int hg_slab_barrier(hg_ctx* c, bool push);   // generation signal + all-rank wait, with or without the edge-row push
 int hg_slab_wait_pending(hg_ctx* c); // enqueue the wait for the last signalled generation (before rain / a step touches the planes)
 int hg_slab_check_sticky(hg_ctx* c); // HG_ERR_STATE once a halo wait has timed out on this context

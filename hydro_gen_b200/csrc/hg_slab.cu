@@ -25,7 +25,7 @@ struct PushSide {
     float* dst[HG_NPLANES];         // neighbour's planes (same set), local row 0; nullptr = no neighbour on this side
     size_t src_off, dst_off;        // element offsets of the first row to copy
 };
-struct FlagArgs { unsigned* flag[HG_MAX_SLABS]; int n; };
+typedef HgFlagArgs FlagArgs;
 struct PushArgs {
     const float* src[HG_NPLANES];   // my planes (current read set), local row 0
     PushSide side[2];
@@ -285,7 +285,43 @@ int hg_slab_check_sticky(hg_ctx* c) {
     return HG_OK;
 }
 
-int hg_slab_exchange(hg_ctx* c) { return hg_slab_barrier(c, true); }
+// After a fused step.  When the step's own kernels already stored the edge rows into the neighbours' ghost rows and
+// signalled the generation (hg_fused.cu: fused push), only the bookkeeping is left.
+int hg_slab_exchange(hg_ctx* c) {
+    if (c->fused_push_gen) {
+        c->pending_gen = c->fused_push_gen;
+        c->fused_push_gen = 0;
+        return HG_OK;
+    }
+    return hg_slab_barrier(c, true);
+}
+
+int hg_slab_peer_planes(const hg_ctx* c, float* out[2][HG_NPLANES], int* mask) {
+    const HgSlabTable& T = c->slabs;
+    *mask = 0;
+    for (int s = 0; s < 2; s++) {
+        const int nb = T.me + (s == 0 ? -1 : 1);
+        for (int p = 0; p < HG_NPLANES; p++) out[s][p] = nullptr;
+        if (nb < 0 || nb >= T.n) continue;
+        *mask |= 1 << s;
+        const size_t nb_elems = plane_elems_of(c, nb);
+        // my local row r (ghost rows included) of the first owned rows is the lower neighbour's local row r + rows[nb];
+        // of the last owned rows (local rows [rows, rows + HALO)) the upper neighbour's local row r - rows
+        const ptrdiff_t shift = s == 0 ? (ptrdiff_t)T.rows[nb] * c->g.pitch : -(ptrdiff_t)c->g.rows * c->g.pitch;
+        for (int p = 0; p < HG_NPLANES; p++) {
+            const int dst_set = c->ri[hg_field_of_plane(p)] ^ 1;      // a fused step writes the other set of every field
+            out[s][p] = T.arena[nb] + ((size_t)dst_set * HG_NPLANES + p) * nb_elems + shift;
+        }
+    }
+    return HG_OK;
+}
+void hg_slab_signal_args(const hg_ctx* c, HgFlagArgs* out) {
+    const HgSlabTable& T = c->slabs;
+    memset(out, 0, sizeof(*out));
+    out->n = T.n;
+    for (int k = 0; k < T.n; k++)
+        if (k != T.me) out->flag[k] = flag_ptr(T.arena[k], plane_elems_of(c, k), T.me);
+}
 static int slab_generation(hg_ctx* c, int mode);
 int hg_slab_barrier(hg_ctx* c, bool push) { return slab_generation(c, push ? 1 : 0); }
 int hg_slab_push_images(hg_ctx* c) { return slab_generation(c, 2); }
