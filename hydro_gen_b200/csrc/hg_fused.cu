@@ -33,6 +33,14 @@
 #define HG_FREE_UNROLL 1
 #endif
 constexpr int kFreeUnroll = HG_FREE_UNROLL;
+// steady-state row loop of k_fused_ws per warp group (measured: anything above 1 leaves the instruction cache)
+#ifndef HG_UNROLL_H
+#define HG_UNROLL_H 1
+#endif
+#ifndef HG_UNROLL_T
+#define HG_UNROLL_T 1
+#endif
+constexpr int kUnrollH = HG_UNROLL_H, kUnrollT = HG_UNROLL_T;
 constexpr int HG_MAX_DEVICES = 64;
 #ifndef HG_FUSED_DEFAULT_VARIANT
 #define HG_FUSED_DEFAULT_VARIANT 5     // 5: one column per thread (k_fused_ws); 10: two columns per thread (k_fused_ws2)
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
-#pragma unroll 1
+#pragma unroll kUnrollH
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_H(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
 #undef HG_ROW_H
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
-#pragma unroll 1
+#pragma unroll kUnrollT
         for (; i <= pl.free_hi; i++, off += pitch) HG_ROW_T(true)
         for (; i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
 #undef HG_ROW_T

@@ -38,3 +38,28 @@ def test_random_shapes_and_parameters(built, seed):
     for fid, name in ((0, "heightmap"), (1, "flux"), (3, "sediment")):
         assert_bit_equal(ctx.download(fid), ref.get(fid), f"seed {seed} {W}x{H}: {name}")
     ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("variant,shape", [(10, (264, 200)), (13, (264, 200)), (15, (136, 72)), (18, (264, 200)), (18, (120, 40)), (19, (400, 136)),
+                                           (21, (264, 200)), (22, (264, 200)), (22, (400, 72)), (24, (400, 136))])
+def test_tuning_variants_of_the_fused_kernel_are_bit_exact(built, monkeypatch, variant, shape):
+    """The non-default forms of the fused step kernel kept in the tree as measured variants (HG_FUSED_VARIANT, read when a
+    context is created): two columns per thread (10), three warp groups (13, 15), queued thermal outflow with one / two
+    service warps (18, 19; 24 on 192-column strips), warp groups swapped (21), 192-column strips (22) -- each against the
+    oracle over 10 main-loop steps with rain, bit for bit, on maps that are not a multiple of the strip width."""
+    W, H = shape
+    monkeypatch.setenv("HG_FUSED_VARIANT", str(variant))
+    ref = oracle.World(W, H, seed=77.25)
+    ref.rain.period = 3
+    ref.gen_heightmap()
+    ctx = Context(W, H)
+    ctx.set_map(_lib.MapSettingsData.from_buffer_copy(bytes(ref.map)))
+    ctx.set_rain(_lib.RainData.from_buffer_copy(bytes(ref.rain)))
+    ctx.gen_heightmap()
+    for s in range(1, 11):
+        t = float(np.float32(s) * np.float32(DT_TIME))
+        ref.step(t)
+        ctx.run(1, t, 0.0, True)
+    for fid, name in ((0, "heightmap"), (1, "flux"), (3, "sediment")):
+        assert_bit_equal(ctx.download(fid), ref.get(fid), f"variant {variant} {W}x{H}: {name}")
+    ctx.close(); ref.close()
