@@ -47,21 +47,19 @@ HG_FN float hg_smoothstep(float e0, float e1, float x) {
  * single-precision Cephes scheme), about 2 ulp. */
 HG_FN float hg_atanf(float xx) {
     float x = fabsf(xx);
-    float y;
-    if (x > 2.414213562373095f) {
-        y = 1.5707963267948966f;
-        x = -(1.0f / x);
-    } else if (x > 0.4142135623730950f) {
-        y = 0.7853981633974483f;
-        x = (x - 1.0f) / (x + 1.0f);
-    } else {
-        y = 0.0f;
-    }
+    /* The three ranges as ONE division: -(1/x) = (-1)/x and x = x/1 exactly (IEEE division is sign-symmetric and
+     * division by one is exact), so selecting numerator and denominator gives the bits of the three-branch form --
+     * one division instead of two in the warp-divergent code of the thermal outflow path. */
+    const int hi = x > 2.414213562373095f, mid = x > 0.4142135623730950f;
+    const float y = hi ? 1.5707963267948966f : (mid ? 0.7853981633974483f : 0.0f);
+    const float num = hi ? -1.0f : (mid ? x - 1.0f : x);
+    const float den = hi ? x : (mid ? x + 1.0f : 1.0f);
+    x = num / den;
     float z = x * x;
     float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z
                - 3.33329491539e-1f) * z * x + x;
-    y = y + p;
-    return (xx < 0.0f) ? -y : y;
+    const float r = y + p;
+    return (xx < 0.0f) ? -r : r;
 }
 
 /* exp(x) for |x| < 80: x = n ln2 + r, degree-5 polynomial on r, scale by 2^n. */
