@@ -201,6 +201,27 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// The same with shared-window addresses formed once outside the row loop (the generic-to-shared conversion of a pointer
+// costs a special-register read and two uniform operations every time it is repeated).
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HG_WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra HG_DONEA_%=;\n"
+        "bra HG_WAITA_%=;\n"
+        "HG_DONEA_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(unsigned dst, const CUtensorMap* map, unsigned bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // Shared block: [raw ring: 2 slots x 9 planes x (NT+4) floats, each 128-byte aligned][row rings][2 mbarriers]
 template <int NT> struct FusedSmem {
     static constexpr size_t RAW_BOX = (size_t)HGF_NPL * HGF_RAW_LD(NT);             // floats delivered per box
@@ -334,14 +355,18 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     int i = pl.i_begin;
     if (hydro) {
         if (RH < RT) reg_dec<RH>(); else if (RH > RT) reg_inc<RH>();      // droplet mode gives the hydraulic group the larger share
+        unsigned bar_a = smem_u32(bars), raw_a = smem_u32(smb);      /* loop-invariant shared-window addresses, */
+        asm volatile("" : "+r"(bar_a), "+r"(raw_a));                       /* opaque so that they are kept, not re-derived every row */
 #define HG_ROW_H(FREEFLAG)                                                                                           \
     {                                                                                                                \
         const int rel = i - pl.i_begin;                                                                              \
         if (tid == 0 && i < pl.i_end) {                                                                              \
-            mbar_expect_tx(&bars[(rel + 1) & 1], BOX_BYTES);                                                         \
-            HG_TMA_ROW(smb + ((rel + 1) & 1) * FusedSmem<NT>::RAW_SLOT, &bars[(rel + 1) & 1], ly0 + rel + 1);       \
+            const unsigned nb = bar_a + (((unsigned)rel + 1u) & 1u) * 8u;                                            \
+            const unsigned nd = raw_a + (((unsigned)rel + 1u) & 1u) * (unsigned)(FusedSmem<NT>::RAW_SLOT * sizeof(float)); \
+            mbar_expect_tx_a(nb, BOX_BYTES);                                                                         \
+            if (DROPS) tma_load_3d_a(nd, &tmap, nb, 0, bx0, ly0 + rel + 1); else tma_load_3d_a(nd, &tmap, nb, bx0, ly0 + rel + 1, 0); \
         }                                                                                                            \
-        mbar_wait(&bars[rel & 1], (unsigned)(rel >> 1) & 1u);                                                        \
+        mbar_wait_a(bar_a + ((unsigned)rel & 1u) * 8u, ((unsigned)rel >> 1) & 1u);                                   \
         hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
         cta_barrier();                                                                                               \
     }
