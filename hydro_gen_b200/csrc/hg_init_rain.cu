@@ -31,29 +31,39 @@ __global__ void __launch_bounds__(256) k_heightmap(SlabDom d, hg_map_settings_da
     for (int k = 0; k < A.nzero; k++) A.zero[k][i] = 0.0f;
 }
 
+#ifndef HG_RAIN_ROWS_PER_THREAD
+#define HG_RAIN_ROWS_PER_THREAD 4
+#endif
 struct RainArgs { const float *rock, *dirt, *water, *total; float *o_rock, *o_dirt, *o_water, *o_total; };
 
 __global__ void __launch_bounds__(256) k_rain(SlabDom d, hg_rain_data set, hg_map_settings_data map_set, float time, RainArgs A) {
     // the permute tables of the table-form simplex noise (hg_noise.cuh): permute(k), k = 0..579, as int and as float
     __shared__ int perm_i[HG_PERM_N];
     __shared__ float perm_f[HG_PERM_N];
+    __shared__ __align__(16) HgGrad perm_g[HG_PERM_N];      // gradient of permute(k): one 16-byte load per simplex corner
     for (int k = threadIdx.y * blockDim.x + threadIdx.x; k < HG_PERM_N; k += blockDim.x * blockDim.y) {
         const float p = hg_permute((float)k);
         perm_f[k] = p; perm_i[k] = (int)p;
+        perm_g[k] = hg_simplex_grad(p);
     }
     __syncthreads();
-    const HgPermTab T{perm_i, perm_f};
+    const HgPermTab T{perm_i, perm_f, perm_g};
+    // HG_RAIN_ROWS_PER_THREAD rows per thread, blockDim.y apart: the table fill above is paid once for that many cells
     int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int gy = d.row0 - HG_HALO_ROWS + (int)(blockIdx.y * blockDim.y + threadIdx.y);
-    if (x >= d.W || gy < 0 || gy >= d.H || gy >= d.row0 + d.rows + HG_HALO_ROWS) return;
-    size_t i = sidx(d, x, gy);
-    float rock = A.rock[i], dirt = A.dirt[i], water = A.water[i];
-    // H.a as its last writer left it: (rock + dirt) + water (smoothing.glsl:101, rain.glsl:54,
-    // heightmap.glsl:146); read back when the PASSES schedule materialises it
-    float total = A.total ? A.total[i] : rock + dirt + water;
-    water += hg_rain_cell(set, map_set, time, x, gy, total, &T);
-    A.o_rock[i] = rock; A.o_dirt[i] = dirt; A.o_water[i] = water;
-    if (A.o_total) A.o_total[i] = rock + dirt + water;
+    if (x >= d.W) return;
+#pragma unroll 1
+    for (int r = 0; r < HG_RAIN_ROWS_PER_THREAD; r++) {
+        int gy = d.row0 - HG_HALO_ROWS + (int)((blockIdx.y * HG_RAIN_ROWS_PER_THREAD + r) * blockDim.y + threadIdx.y);
+        if (gy < 0 || gy >= d.H || gy >= d.row0 + d.rows + HG_HALO_ROWS) continue;
+        size_t i = sidx(d, x, gy);
+        float rock = A.rock[i], dirt = A.dirt[i], water = A.water[i];
+        // H.a as its last writer left it: (rock + dirt) + water (smoothing.glsl:101, rain.glsl:54,
+        // heightmap.glsl:146); read back when the PASSES schedule materialises it
+        float total = A.total ? A.total[i] : rock + dirt + water;
+        water += hg_rain_cell(set, map_set, time, x, gy, total, &T);
+        A.o_rock[i] = rock; A.o_dirt[i] = dirt; A.o_water[i] = water;
+        if (A.o_total) A.o_total[i] = rock + dirt + water;
+    }
 }
 
 }  // namespace
@@ -81,7 +91,7 @@ int hg_launch_rain(hg_ctx* c, float time) {
         if (rcw) return rcw;
     }
     SlabDom d{c->g.W, c->g.H, c->g.pitch, c->g.row0, c->g.rows};
-    dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 7) / 8);
+    dim3 b(32, 8), g((c->g.W + 31) / 32, (c->g.rows_alloc + 8 * HG_RAIN_ROWS_PER_THREAD - 1) / (8 * HG_RAIN_ROWS_PER_THREAD));
     // The reference writes the other heightmap texture and swaps (erosion.cpp:76-89).  Rain is
     // pointwise, so on the FUSED schedule it runs in place: H, F and S then stay in the same
     // ping-pong set, which the fused kernel's nine-plane TMA box needs.

@@ -75,7 +75,21 @@ HG_FN float hg_simplex(float vx, float vy) {
 // loads instead of 7 x (3 multiply-adds + a 6-instruction mod 289).  The permute chain was 40 % of k_rain's
 // instructions (profiles/r01i_all_kernels.txt: 92 % of issue slots busy).
 constexpr int HG_PERM_N = 580;
-struct HgPermTab { const int* ti; const float* tf; };      // permute(k) as int and as float
+// The gradient of a corner depends on its hash alone: (a, h) = the two components gln_simplex derives from
+// p = permute(k) and the normalisation factor 1.79284291400159 - 0.85373472095314 (a a + h h), formed by the same
+// operations in the same order (hg_simplex_grad), so the 12 operations per corner become one 16-byte load.
+struct HgGrad { float a, h, nrm, pad; };
+HG_FN HgGrad hg_simplex_grad(float p) {
+    const float Cw = 0.024390243902439f;
+    const float q = 2.0f * hg_fract(p * Cw) - 1.0f;
+    HgGrad g;
+    g.h = fabsf(q) - 0.5f;
+    g.a = q - floorf(q + 0.5f);
+    g.nrm = 1.79284291400159f - 0.85373472095314f * (g.a * g.a + g.h * g.h);
+    g.pad = 0.0f;
+    return g;
+}
+struct HgPermTab { const int* ti; const float* tf; const HgGrad* tg; };      // permute(k) as int and as float; gradient of permute(k) (null: computed)
 HG_FN int hg_imod289(int v) { int r = v % 289; return r < 0 ? r + 289 : r; }
 HG_FN float hg_simplex_tab(float vx, float vy, const HgPermTab& T) {
     const float Cx = 0.211324865405187f, Cy = 0.366025403784439f;
@@ -94,14 +108,21 @@ HG_FN float hg_simplex_tab(float vx, float vy, const HgPermTab& T) {
     if (!(fabsf(ix) < 1.0e9f && fabsf(iy) < 1.0e9f)) return hg_simplex(vx, vy);
     const int jx = hg_imod289((int)ix), jy = hg_imod289((int)iy);      // == mod289(ix), mod289(iy): exact integers
     const int in0 = T.ti[jy], in2 = T.ti[jy + 1];
-    float p0 = T.tf[in0 + jx];
-    float p1 = T.tf[(hi ? in0 : in2) + jx + (hi ? 1 : 0)];
-    float p2 = T.tf[in2 + jx + 1];
+    const int k0 = in0 + jx, k1 = (hi ? in0 : in2) + jx + (hi ? 1 : 0), k2 = in2 + jx + 1;
     float m0 = hg_max(0.5f - (x0x * x0x + x0y * x0y), 0.0f);
     float m1 = hg_max(0.5f - (x1x * x1x + x1y * x1y), 0.0f);
     float m2 = hg_max(0.5f - (x2x * x2x + x2y * x2y), 0.0f);
     m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
     m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
+    if (T.tg) {
+        const HgGrad G0 = T.tg[k0], G1 = T.tg[k1], G2 = T.tg[k2];
+        m0 *= G0.nrm; m1 *= G1.nrm; m2 *= G2.nrm;
+        const float g0 = G0.a * x0x + G0.h * x0y;
+        const float g1 = G1.a * x1x + G1.h * x1y;
+        const float g2 = G2.a * x2x + G2.h * x2y;
+        return 130.0f * (m0 * g0 + m1 * g1 + m2 * g2);
+    }
+    float p0 = T.tf[k0], p1 = T.tf[k1], p2 = T.tf[k2];
     float q0 = 2.0f * hg_fract(p0 * Cw) - 1.0f;
     float q1 = 2.0f * hg_fract(p1 * Cw) - 1.0f;
     float q2 = 2.0f * hg_fract(p2 * Cw) - 1.0f;

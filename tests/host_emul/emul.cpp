@@ -111,8 +111,9 @@ void emul_heightmap(const hg_map_settings_data* cfg, int W, int H, float* rock, 
 long emul_simplex_tab_mismatches(const float* xs, const float* ys, long n) {
     static int ti[HG_PERM_N];
     static float tf[HG_PERM_N];
-    for (int k = 0; k < HG_PERM_N; k++) { tf[k] = hg_permute((float)k); ti[k] = (int)tf[k]; }
-    HgPermTab T{ti, tf};
+    static HgGrad tg[HG_PERM_N];
+    for (int k = 0; k < HG_PERM_N; k++) { tf[k] = hg_permute((float)k); ti[k] = (int)tf[k]; tg[k] = hg_simplex_grad(tf[k]); }
+    HgPermTab T{ti, tf, tg};
     long bad = 0;
     for (long i = 0; i < n; i++) {
         float a = hg_simplex(xs[i], ys[i]), b = hg_simplex_tab(xs[i], ys[i], T);
