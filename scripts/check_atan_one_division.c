@@ -13,14 +13,16 @@ static inline float old_atanf(float xx) {
     y = y + p;
     return (xx < 0.0f) ? -y : y;
 }
-int main(void) {
+#include <stdlib.h>
+int main(int argc, char** argv) {
+    const unsigned long long step = argc > 1 ? strtoull(argv[1], 0, 10) : 1ull;      /* 1 = exhaustive; a prime > 1 = a sample (the CPU test suite) */
     unsigned long long bad = 0;
 #pragma omp parallel for reduction(+ : bad)
-    for (unsigned long long u = 0; u <= 0xffffffffull; u++) {
+    for (unsigned long long u = 0; u <= 0xffffffffull; u += step) {
         uint32_t b = (uint32_t)u; float x; memcpy(&x, &b, 4);
         float a = old_atanf(x), c = hg_atanf(x);
         if (memcmp(&a, &c, 4)) { if (!(a != a && c != c)) bad++; }
     }
-    printf("old vs one-division hg_atanf over all 2^32 bit patterns: %llu mismatches (NaN results compared as NaN)\n", bad);
+    printf("old vs one-division hg_atanf over every %llu-th of the 2^32 bit patterns: %llu mismatches (NaN results compared as NaN)\n", step, bad);
     return bad != 0;
 }

@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
-int main(void) {
+#include <stdlib.h>
+int main(int argc, char** argv) {
+    const uint32_t step = argc > 1 ? (uint32_t)strtoul(argv[1], 0, 10) : 1u;      /* 1 = exhaustive */
     const float c = 1e-12f;
     uint32_t lo = 0, hi = 0x7f800000u;   // smallest bits with sqrtf(x) >= c
     while (lo < hi) { uint32_t mid = lo + (hi - lo) / 2; float x; memcpy(&x, &mid, 4); if (sqrtf(x) >= c) hi = mid; else lo = mid + 1; }
@@ -12,7 +14,7 @@ int main(void) {
     printf("T bits 0x%08x = %.9g ; sqrtf(T) = %.9g, sqrtf(prev) = %.9g, c = %.9g\n", lo, T, sqrtf(T), sqrtf(nextafterf(T, 0)), c);
     // exhaustive check over all non-negative floats
     unsigned long long bad = 0;
-    for (uint32_t b = 0; b < 0x7f800000u; b++) { float x; memcpy(&x, &b, 4); if ((sqrtf(x) < c) != (x < T)) bad++; }
+    for (uint64_t b64 = 0; b64 < 0x7f800000ull; b64 += step) { uint32_t b = (uint32_t)b64; float x; memcpy(&x, &b, 4); if ((sqrtf(x) < c) != (x < T)) bad++; }
     printf("mismatches: %llu\n", bad);
     return 0;
 }
