@@ -101,6 +101,45 @@ template <int NT> struct HgRings {
     static constexpr int TOTAL = TOTAL_BYTES / 4;    // 74 * E floats
 };
 
+// (a.x - b.x) + (a.y - b.y).  Device: the two subtractions as one FADD2 (add.rn.f32x2 with a negated operand: each lane
+// rounded like the scalar instruction, DESIGN.md §3.1 "two columns per thread"), then the scalar sum.
+HG_FN float hg_pair_diff_sum(const HgF2& a, const HgF2& b) {
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__) && !defined(HG_NO_PACKED_DIFF)
+    const float2 d = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    return d.x + d.y;
+#else
+    return (a.x - b.x) + (a.y - b.y);
+#endif
+}
+
+// hg_smooth_cell on the (rock, dirt) pairs the G2 ring holds.  Device: the eight differences and the two five-point sums
+// as packed additions (same operations, same association, each lane rounded like the scalar instruction); everything
+// else is hg_smooth_cell's code.  Host: hg_smooth_cell itself.
+HG_FN void hg_smooth_pair(const HgStepParams& P, float& rock, float& dirt, const HgF2& own, const HgF2& l, const HgF2& r, const HgF2& t, const HgF2& b) {
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__) && !defined(HG_NO_PACKED_DIFF)
+    const float2 o = make_float2(own.x, own.y);
+    const float2 dl = __fadd2_rn(o, make_float2(-l.x, -l.y)), dr = __fadd2_rn(o, make_float2(-r.x, -r.y));
+    const float2 dt = __fadd2_rn(o, make_float2(-t.x, -t.y)), db = __fadd2_rn(o, make_float2(-b.x, -b.y));
+    const float dlr = dl.x, drr = dr.x, dtr = dt.x, dbr = db.x;
+    const float dlg = dl.y + dlr, drg = dr.y + drr, dtg = dt.y + dtr, dbg = db.y + dbr;
+    const float g_hdiff = fabsf((dlg + drg + dtg + dbg) / 4.0f);
+    const float r_hdiff = fabsf((dlr + drr + dtr + dbr) / 4.0f);
+    const float xcr = dlr * drr, xcg = dlg * drg;
+    const float ycr = dtr * dbr, ycg = dtg * dbg;
+    // terr + l + r + t + b for both layers at once
+    const float2 s5 = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(o, make_float2(l.x, l.y)), make_float2(r.x, r.y)), make_float2(t.x, t.y)), make_float2(b.x, b.y));
+    float terr_r = own.x, terr_g = own.y;
+    if ((((-dlr) > r_hdiff || (-drr) > r_hdiff) && xcr > 0.0f) || (((-dtr) > r_hdiff || (-dbr) > r_hdiff) && ycr > 0.0f)) terr_r = hg_div5(s5.x);
+    if ((((-dlg) > g_hdiff || (-drg) > g_hdiff) && xcg > 0.0f) || (((-dtg) > g_hdiff || (-dbg) > g_hdiff) && ycg > 0.0f)) terr_g = hg_div5(s5.y);
+    const float m = P.smooth_mul;
+    rock = m * terr_r + (1.0f - m) * own.x;
+    dirt = m * terr_g + (1.0f - m) * own.y;
+#else
+    rock = own.x; dirt = own.y;
+    hg_smooth_cell(P, rock, dirt, l.x, l.y, r.x, r.y, t.x, t.y, b.x, b.y);
+#endif
+}
+
 struct HgPlanItem { int strip, gy0, gy1, pad; };
 
 struct HgFusedK {
@@ -283,8 +322,8 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             const char* const r1 = (up ? B8(3) : B8(2)) + R::SS + cdx * 8;
             const HgF2 t00 = reinterpret_cast<const HgF2*>(r0)[0], t10 = reinterpret_cast<const HgF2*>(r0)[1];
             const HgF2 t01 = reinterpret_cast<const HgF2*>(r1)[0], t11 = reinterpret_cast<const HgF2*>(r1)[1];
-            float sr = hg_bilerp(t00.x, t10.x, t01.x, t11.x, b.sx, b.sy);
-            float sd = hg_bilerp(t00.y, t10.y, t01.y, t11.y, b.sx, b.sy);
+            float sr, sd;
+            hg_bilerp2(t00.x, t00.y, t10.x, t10.y, t01.x, t01.y, t11.x, t11.y, b.sx, b.sy, sr, sd);
             if (owned) {
                 const unsigned idx = off - 3u * pitch;
                 if (fast) {
@@ -360,10 +399,11 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
         if (FREE || (ye >= gy0 - 2 && ye < gy1 + 2)) {
             const bool in = xin && (FREE || (ye >= 0 && ye < H));
             float out[8], d_h[8];
-            d_h[0] = (w11.x - w10.x) + (w11.y - w10.y); d_h[1] = (w11.x - w12.x) + (w11.y - w12.y);
-            d_h[2] = (w11.x - w21.x) + (w11.y - w21.y); d_h[3] = (w11.x - w01.x) + (w11.y - w01.y);
-            d_h[4] = (w11.x - w20.x) + (w11.y - w20.y); d_h[5] = (w11.x - w22.x) + (w11.y - w22.y);
-            d_h[6] = (w11.x - w00.x) + (w11.y - w00.y); d_h[7] = (w11.x - w02.x) + (w11.y - w02.y);
+            // (rock1 - n.rock1) + (dirtE - n.dirtE): the two differences are one packed subtraction on the pair the ring holds
+            d_h[0] = hg_pair_diff_sum(w11, w10); d_h[1] = hg_pair_diff_sum(w11, w12);
+            d_h[2] = hg_pair_diff_sum(w11, w21); d_h[3] = hg_pair_diff_sum(w11, w01);
+            d_h[4] = hg_pair_diff_sum(w11, w20); d_h[5] = hg_pair_diff_sum(w11, w22);
+            d_h[6] = hg_pair_diff_sum(w11, w00); d_h[7] = hg_pair_diff_sum(w11, w02);
             so1 = hg_thermal_outflow(P, 1, w11.y, d_h, out, in);
             T1 = out[2]; B1 = out[3];
             HgF4 tr; tr.x = out[1]; tr.y = out[5]; tr.z = out[7]; tr.w = 0.0f;
@@ -403,8 +443,8 @@ HG_FN void hg_fused_iter(HgCol& c, float* sm, const float* raw, const HgFusedK& 
             const HgF2 l = Q2(R::G2, 11, -1), r = Q2(R::G2, 11, 1);
             const HgF2 dn = Q2(R::G2, 12, 0), own = Q2(R::G2, 11, 0), up = Q2(R::G2, 10, 0);
             float rock = own.x, dirt = own.y;
-            float sr_ = rock, sd_ = dirt;
-            hg_smooth_cell(P, sr_, sd_, l.x, l.y, r.x, r.y, up.x, up.y, dn.x, dn.y);
+            float sr_, sd_;
+            hg_smooth_pair(P, sr_, sd_, own, l, r, up, dn);
             const bool border = (x == 0 || x == W - 1 || (!FREE && (yg == 0 || yg == H - 1)));
             if (owned) {
                 const unsigned idx = off - (unsigned)HGF_LAG_G * pitch;
