@@ -124,16 +124,17 @@ HG_FN void hg_smooth_pair(const HgStepParams& P, float& rock, float& dirt, const
     const float dlg = dl.y + dlr, drg = dr.y + drr, dtg = dt.y + dtr, dbg = db.y + dbr;
     const float g_hdiff = fabsf((dlg + drg + dtg + dbg) / 4.0f);
     const float r_hdiff = fabsf((dlr + drr + dtr + dbr) / 4.0f);
-    const float xcr = dlr * drr, xcg = dlg * drg;
-    const float ycr = dtr * dbr, ycg = dtg * dbg;
+    const float2 xc = __fmul2_rn(make_float2(dlr, dlg), make_float2(drr, drg)), yc = __fmul2_rn(make_float2(dtr, dtg), make_float2(dbr, dbg));
+    const float xcr = xc.x, xcg = xc.y, ycr = yc.x, ycg = yc.y;
     // terr + l + r + t + b for both layers at once
     const float2 s5 = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(o, make_float2(l.x, l.y)), make_float2(r.x, r.y)), make_float2(t.x, t.y)), make_float2(b.x, b.y));
     float terr_r = own.x, terr_g = own.y;
     if ((((-dlr) > r_hdiff || (-drr) > r_hdiff) && xcr > 0.0f) || (((-dtr) > r_hdiff || (-dbr) > r_hdiff) && ycr > 0.0f)) terr_r = hg_div5(s5.x);
     if ((((-dlg) > g_hdiff || (-drg) > g_hdiff) && xcg > 0.0f) || (((-dtg) > g_hdiff || (-dbg) > g_hdiff) && ycg > 0.0f)) terr_g = hg_div5(s5.y);
-    const float m = P.smooth_mul;
-    rock = m * terr_r + (1.0f - m) * own.x;
-    dirt = m * terr_g + (1.0f - m) * own.y;
+    const float m = P.smooth_mul, m1 = 1.0f - m;
+    const float2 pa = __fmul2_rn(make_float2(m, m), make_float2(terr_r, terr_g)), pb = __fmul2_rn(make_float2(m1, m1), o);
+    rock = __fadd_rn(pa.x, pb.x);      // scalar sums: a packed add of packed products would be fused by ptxas
+    dirt = __fadd_rn(pa.y, pb.y);
 #else
     rock = own.x; dirt = own.y;
     hg_smooth_cell(P, rock, dirt, l.x, l.y, r.x, r.y, t.x, t.y, b.x, b.y);
