@@ -309,13 +309,16 @@ __device__ __forceinline__ void cta_barrier() {
 }
 
 // SWAP: the hydraulic group on the upper half of the CTA's warps (the SM's warp arbiter prefers the higher warp id).
-template <int NT, int MINB, int RH, int RT, bool DROPS, bool SWAP = false>
+template <int NT, int MINB, int RH, int RT, bool DROPS, int SWAP = 0>
 __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant__ HgFusedK K, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) float smb[];
     float* const sm = smb + FusedSmem<NT>::RINGS;
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(smb + FusedSmem<NT>::BARS);
-    const bool hydro = SWAP ? threadIdx.x >= NT : threadIdx.x < NT;
-    const int tid = threadIdx.x < NT ? threadIdx.x : threadIdx.x - NT;
+    // SWAP 2: the groups interleaved in pairs of warps (warps 0,1 | 4,5 hydraulic, 2,3 | 6,7 thermal), so that a scheduler
+    // (warp id mod 4) only ever runs ONE of the two loops; needs RH == RT (setmaxnreg works on whole warpgroups)
+    static_assert(SWAP != 2 || (RH == RT && NT % 64 == 0), "interleaved groups cannot rebalance registers");
+    const bool hydro = SWAP == 2 ? ((threadIdx.x >> 6) & 1) == 0 : SWAP == 1 ? threadIdx.x >= NT : threadIdx.x < NT;
+    const int tid = SWAP == 2 ? (int)(((threadIdx.x >> 7) << 6) + (threadIdx.x & 63)) : threadIdx.x < NT ? threadIdx.x : threadIdx.x - NT;
     int strip, gy0, gy1;
     if (K.plan) {           // balanced partition (hg_plan_*): this CTA's strip and rows come from the plan
         const HgPlanItem it = K.plan[blockIdx.x];
@@ -831,7 +834,7 @@ static int launch_main(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     return HG_OK;
 }
 
-template <int NT, int MINB, int RH, int RT, bool DROPS = false, bool SWAP = false>
+template <int NT, int MINB, int RH, int RT, bool DROPS = false, int SWAP = 0>
 static int launch_ws(hg_ctx* c, const HgFusedK& K0, int seg, int src_set) {
     static_assert((RH + RT) / 2 * 2 * NT * MINB <= 65536 && RH % 8 == 0 && RT % 8 == 0, "register budget of the two warp groups");
     HgFusedK K = K0;
@@ -1031,10 +1034,11 @@ static int launch_fused(hg_ctx* c, bool drops) {
     // variants 13..: three warp groups per CTA (k_fused_ws3)
     // variants 18..: queued thermal outflow with service warps (k_fused_q)
     // variants 21..23: k_fused_ws with the groups swapped / 192-column strips
-    constexpr int NVAR = 25;
-    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 192, 192, 192};
-    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2};
-    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 12, 12, 12, 12, 12, 9, 10, 12, 8, 12, 12, 13};
+    // variants 25, 26: k_fused_ws without register rebalancing (80 / 80), groups interleaved in warp pairs / in order
+    constexpr int NVAR = 27;
+    static const int nt_of[NVAR] = {128, 128, 192, 224, 224, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 192, 192, 192, 128, 128};
+    static const int res_of[NVAR] = {4, 3, 2, 2, 1, 3, 2, 3, 4, 4, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2, 2, 2, 3, 3};
+    static const int wpc_of[NVAR] = {4, 4, 6, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 12, 12, 12, 12, 12, 9, 10, 12, 8, 12, 12, 13, 8, 8};
     int v = c->tune_variant >= 0 && c->tune_variant < NVAR ? c->tune_variant : HG_FUSED_DEFAULT_VARIANT;
     if (drops) v = c->tune_drops_variant == 1 ? 3 : c->tune_drops_variant == 2 ? 13 : c->tune_drops_variant == 3 ? 18 : 5;      // HG_DROPS_VARIANT=1: one warp group of 224 threads runs every stage; 2: three groups
     const bool two_lane = v >= 10 && v < 13;
@@ -1129,10 +1133,12 @@ static int launch_fused(hg_ctx* c, bool drops) {
     case 18: rc = drops ? launch_q<128, 3, 1, true>(c, K, seg, c->ri[0]) : launch_q<128, 3, 1>(c, K, seg, c->ri[0]); break;
     case 19: rc = launch_q<128, 3, 2>(c, K, seg, c->ri[0]); break;
     case 20: rc = launch_q<128, 3, 4>(c, K, seg, c->ri[0]); break;
-    case 21: rc = launch_ws<128, 3, 72, 88, false, true>(c, K, seg, c->ri[0]); break;
+    case 21: rc = launch_ws<128, 3, 72, 88, false, 1>(c, K, seg, c->ri[0]); break;
     case 22: rc = launch_ws<192, 2, 80, 80>(c, K, seg, c->ri[0]); break;      // (setmaxnreg works on whole warpgroups of 4 warps: a 6 + 6 warp CTA cannot rebalance)
-    case 23: rc = launch_ws<192, 2, 80, 80, false, true>(c, K, seg, c->ri[0]); break;
-    default: rc = launch_q<192, 2, 1>(c, K, seg, c->ri[0]); break;
+    case 23: rc = launch_ws<192, 2, 80, 80, false, 1>(c, K, seg, c->ri[0]); break;
+    case 24: rc = launch_q<192, 2, 1>(c, K, seg, c->ri[0]); break;
+    case 25: rc = launch_ws<128, 3, 80, 80, false, 2>(c, K, seg, c->ri[0]); break;
+    default: rc = launch_ws<128, 3, 80, 80>(c, K, seg, c->ri[0]); break;
     }
     if (rc) return rc;
     if (balanced) {

@@ -41,11 +41,11 @@ def test_random_shapes_and_parameters(built, seed):
 
 
 @pytest.mark.parametrize("variant,shape", [(10, (264, 200)), (13, (264, 200)), (15, (136, 72)), (18, (264, 200)), (18, (120, 40)), (19, (400, 136)),
-                                           (21, (264, 200)), (22, (264, 200)), (22, (400, 72)), (24, (400, 136))])
+                                           (21, (264, 200)), (22, (264, 200)), (22, (400, 72)), (24, (400, 136)), (25, (264, 200)), (26, (136, 72))])
 def test_tuning_variants_of_the_fused_kernel_are_bit_exact(built, monkeypatch, variant, shape):
     """The non-default forms of the fused step kernel kept in the tree as measured variants (HG_FUSED_VARIANT, read when a
     context is created): two columns per thread (10), three warp groups (13, 15), queued thermal outflow with one / two
-    service warps (18, 19; 24 on 192-column strips), warp groups swapped (21), 192-column strips (22) -- each against the
+    service warps (18, 19; 24 on 192-column strips), warp groups swapped (21) or interleaved in pairs of warps (25; 26 is its in-order control), 192-column strips (22) -- each against the
     oracle over 10 main-loop steps with rain, bit for bit, on maps that are not a multiple of the strip width."""
     W, H = shape
     monkeypatch.setenv("HG_FUSED_VARIANT", str(variant))
