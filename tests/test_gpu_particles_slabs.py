@@ -84,15 +84,19 @@ def test_particle_full_step_statistical(built):
     ctx.close(); ref.close()
 
 
-def test_slabs_on_one_gpu_match_whole_map(built):
+@pytest.mark.parametrize("fused_push,cuts", [("1", [0, 96, 168, 256]), ("0", [0, 96, 168, 256]), ("1", [0, 8, 24, 256])])
+def test_slabs_on_one_gpu_match_whole_map(built, monkeypatch, fused_push, cuts):
     """Three row slabs (one context each, same GPU, peer pointers inside the process) step in
     lock step through the device-side halo push + flag wait and must reproduce the whole-map
-    result bit for bit, far fetches across slab boundaries included."""
+    result bit for bit, far fetches across slab boundaries included.  fused_push "1": the step kernel
+    and the fix-up store the edge rows into the neighbours' ghost rows themselves and the fix-up's last
+    block signals (the default); "0": the separate push kernel.  The third case has slabs as thin as the
+    halo (8 and 16 rows): every row of them is an edge row for both neighbours."""
+    monkeypatch.setenv("HG_FUSED_PUSH", fused_push)
     n = 256
     w = wet_world(n, 300)
     whole = Context(n)
     copy_state(w, whole)
-    cuts = [0, 96, 168, 256]
     slabs = [Context(n, n, row0=cuts[i], rows=cuts[i + 1] - cuts[i]) for i in range(3)]
     for i, s in enumerate(slabs):
         s.connect_local(slabs, i)
