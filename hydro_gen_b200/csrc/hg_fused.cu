@@ -356,6 +356,14 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
     HgCol c;
     hg_fused_begin(c);
     int i = pl.i_begin;
+#ifndef HG_NO_RING_ROTATE
+    HgRingOff ro = hg_ring_off<NT>(i, tid);
+#define HG_RO , &ro
+#define HG_RO_NEXT hg_ring_off_next(ro);
+#else
+#define HG_RO
+#define HG_RO_NEXT
+#endif
     if (hydro) {
         if (RH < RT) reg_dec<RH>(); else if (RH > RT) reg_inc<RH>();      // droplet mode gives the hydraulic group the larger share
         unsigned bar_a = smem_u32(bars), raw_a = smem_u32(smb);      /* loop-invariant shared-window addresses, */
@@ -370,7 +378,8 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
             if (DROPS) tma_load_3d_a(nd, &tmap, nb, 0, bx0, ly0 + rel + 1); else tma_load_3d_a(nd, &tmap, nb, bx0, ly0 + rel + 1, 0); \
         }                                                                                                            \
         mbar_wait_a(bar_a + ((unsigned)rel & 1u) * 8u, ((unsigned)rel >> 1) & 1u);                                   \
-        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off); \
+        hg_fused_iter<NT, FREEFLAG, HGF_HYDRO, DROPS>(c, sm, smb + (rel & 1) * FusedSmem<NT>::RAW_SLOT, K, tid, x, xin, owned, gy0, gy1, i, off HG_RO); \
+        HG_RO_NEXT                                                                                                   \
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_H(false)
@@ -387,7 +396,8 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
         if (RH < RT) reg_inc<RT>(); else if (RH > RT) reg_dec<RT>();
 #define HG_ROW_T(FREEFLAG)                                                                                           \
     {                                                                                                                \
-        hg_fused_iter<NT, FREEFLAG, HGF_THERMAL, DROPS>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off);               \
+        hg_fused_iter<NT, FREEFLAG, HGF_THERMAL, DROPS>(c, sm, smb, K, tid, x, xin, owned, gy0, gy1, i, off HG_RO);         \
+        HG_RO_NEXT                                                                                                   \
         cta_barrier();                                                                                               \
     }
         for (; i < pl.free_lo && i <= pl.i_end; i++, off += pitch) HG_ROW_T(false)
@@ -397,6 +407,8 @@ __global__ void __launch_bounds__(2 * NT, MINB) k_fused_ws(const __grid_constant
 #undef HG_ROW_T
 #undef HG_TMA_ROW
     }
+#undef HG_RO
+#undef HG_RO_NEXT
 }
 
 
